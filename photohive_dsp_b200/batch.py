@@ -1,0 +1,212 @@
+"""Batch front door: many same-size 8-bit RGB images per call, one context per GPU.
+
+This is the additive interface the throughput metric is measured on (include/photohive_dsp.h, Part 2).
+Inputs may be numpy uint8 arrays (host) or torch CUDA uint8 tensors (device); the reports come back as
+numpy structured views over the flat records.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lib import lib
+from .structures import phd_flat_head, phd_flat_layout, phd_params
+
+DEFAULTS = dict(h_partitions=18, s_partitions=2, v_partitions=3, black_thresh=0.1, gray_thresh=0.1,
+                coverage_thresh=0.95, linked_list_size=1000, downsample_rate=1, radius_partitions=40,
+                angle_partitions=72, quantity_weight=0.1, saturation_value_weight=0.9,
+                fft_streak_thresh=1.20, magnitude_thresh=0.3, blur_cutoff_ratio_denom=2)
+
+ERRORS = {1: "rejected by the reference's pre-checks", 2: "bad parameters", 3: "no CUDA device", 4: "CUDA error",
+          5: "unsupported size", 6: "image is not 8-bit"}
+
+
+class PhotoHiveError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}: {ERRORS.get(code, '?')}] {msg}")
+        self.code = code
+
+
+def make_params(**kw) -> phd_params:
+    d = dict(DEFAULTS)
+    unknown = set(kw) - set(d)
+    if unknown:
+        raise TypeError(f"unknown parameter(s): {sorted(unknown)}")
+    d.update(kw)
+    return phd_params(**d)
+
+
+def flat_layout(params: phd_params, max_boxes: int = 0) -> phd_flat_layout:
+    lay = phd_flat_layout()
+    rc = lib.phd_flat_get_layout(C.byref(params), max_boxes, C.byref(lay))
+    if rc != 0:
+        raise PhotoHiveError(rc, "cannot lay out records for these parameters")
+    return lay
+
+
+@dataclass
+class BatchReports:
+    """Struct-of-arrays view of n flat records (numpy, host)."""
+    raw: np.ndarray                 # [n, record_bytes] uint8
+    layout: phd_flat_layout
+    rgb_stats: np.ndarray           # [n, 6]
+    average_saturation: np.ndarray  # [n]
+    palette_n: np.ndarray           # [n]
+    palette_hsv: np.ndarray         # [n, T, 3]  (first palette_n[i] rows valid)
+    palette_pct: np.ndarray         # [n, T]
+    parent_ids: np.ndarray          # [n, T]
+    blur_bins: np.ndarray           # [n, na, nr]
+    angle_bin_size: np.ndarray
+    radius_bin_size: np.ndarray
+    blur_vec_angle: np.ndarray      # [n, 10]
+    blur_vec_mag: np.ndarray        # [n, 10]
+    sharpness: np.ndarray | None    # [n, max_boxes]
+    max_power: np.ndarray
+    tie_groups: np.ndarray
+    dropped_pixels: np.ndarray
+
+    def __len__(self):
+        return self.raw.shape[0]
+
+
+def view_records(raw: np.ndarray, lay: phd_flat_layout) -> BatchReports:
+    n = raw.shape[0]
+    T, na, nr, mb = lay.T, lay.na, lay.nr, lay.max_boxes
+    head_dt = np.dtype([("rgb_stats", "<f8", 6), ("average_saturation", "<f8"), ("max_power", "<f8"),
+                        ("dropped_pixels", "<i8"), ("palette_n", "<i4"), ("tie_groups", "<i4"),
+                        ("n_sharpness", "<i4"), ("angle_bin_size", "<i4"), ("radius_bin_size", "<i4"),
+                        ("num_angle_bins", "<i4"), ("num_radius_bins", "<i4"), ("status", "<i4"),
+                        ("blur_vec_angle", "<i4", 10), ("blur_vec_mag", "<f4", 10)])
+    assert head_dt.itemsize == C.sizeof(phd_flat_head)
+
+    def field(off, dtype, count):
+        dt = np.dtype(dtype)
+        return np.ndarray((n, count), dt, raw, offset=off, strides=(raw.strides[0], dt.itemsize))
+
+    head = np.ndarray((n,), head_dt, raw, offset=0, strides=(raw.strides[0],))
+    bad = np.nonzero(head["status"])[0]
+    if bad.size:
+        raise PhotoHiveError(int(head["status"][bad[0]]), f"record {int(bad[0])} is invalid")
+    return BatchReports(
+        raw=raw, layout=lay, rgb_stats=head["rgb_stats"], average_saturation=head["average_saturation"],
+        palette_n=head["palette_n"], palette_hsv=field(lay.off_palette_hsv, "<f8", 3 * T).reshape(n, T, 3),
+        palette_pct=field(lay.off_palette_pct, "<f8", T), parent_ids=field(lay.off_parent_ids, "<i4", T),
+        blur_bins=field(lay.off_blur_bins, "<f8", na * nr).reshape(n, na, nr),
+        angle_bin_size=head["angle_bin_size"], radius_bin_size=head["radius_bin_size"],
+        blur_vec_angle=head["blur_vec_angle"], blur_vec_mag=head["blur_vec_mag"],
+        sharpness=field(lay.off_sharpness, "<f8", mb) if mb > 0 else None, max_power=head["max_power"],
+        tie_groups=head["tie_groups"], dropped_pixels=head["dropped_pixels"])
+
+
+class Context:
+    """One per GPU: owns the stream, FFT/bin-map plans and workspaces of that device."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib.phd_context_create(device, C.byref(h))
+        if rc != 0:
+            raise PhotoHiveError(rc, f"cannot create a context on CUDA device {device}")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.phd_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PhotoHiveError(rc, (lib.phd_last_error(self._h) or b"").decode(errors="replace"))
+
+    # ---- the hot path -----------------------------------------------------------------------------
+    def get_reports(self, images, boxes=None, params: phd_params | None = None, records_out=None,
+                    **param_overrides) -> BatchReports:
+        """images: uint8 [n,H,W,3] numpy array (host) or torch CUDA tensor (device, contiguous).
+        boxes: None or int array [n, max_boxes, 4] of (top, bottom, left, right)."""
+        params = params or make_params(**param_overrides)
+        ptr, n, H, W, stride, keep = _as_image_batch(images)
+        mb, bptr, bkeep = 0, None, None
+        if boxes is not None:
+            bkeep = np.ascontiguousarray(boxes, np.int32)
+            if bkeep.ndim != 3 or bkeep.shape[0] != n or bkeep.shape[2] != 4:
+                raise ValueError("boxes must have shape [n, max_boxes, 4]")
+            mb = bkeep.shape[1]
+            bptr = bkeep.ctypes.data_as(C.c_void_p) if mb > 0 else None
+        lay = flat_layout(params, mb)
+        raw = records_out if records_out is not None else np.empty((n, lay.record_bytes), np.uint8)
+        self._check(lib.phd_get_reports_u8(self._h, ptr, n, W, H, stride, bptr, mb, C.byref(params),
+                                           raw.ctypes.data_as(C.c_void_p)))
+        return view_records(raw, lay)
+
+    def get_reports_raw(self, rgb_ptr: int, n: int, width: int, height: int, stride: int, params: phd_params,
+                        records_ptr: int, boxes_ptr: int | None = None, max_boxes: int = 0) -> None:
+        """Pointer-level call for harnesses that manage their own (pinned / device) buffers."""
+        self._check(lib.phd_get_reports_u8(self._h, rgb_ptr, n, width, height, stride, boxes_ptr, max_boxes,
+                                           C.byref(params), records_ptr))
+
+    def last_timing(self):
+        ms = (C.c_float * 8)()
+        launches = lib.phd_last_timing(self._h, C.byref(ms))
+        names = ["total", "frontend", "palette_select", "palette_accumulate", "fft_rows", "fft_cols_blur",
+                 "sharpness", "finalize"]
+        return dict(zip(names, [float(x) for x in ms])), launches
+
+    # ---- test hooks ---------------------------------------------------------------------------------
+    def debug_group_sweep(self, params: phd_params) -> np.ndarray:
+        out = np.empty(1 << 24, np.uint16)
+        self._check(lib.phd_debug_group_sweep(self._h, C.byref(params), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def debug_bin_map(self, width, height, nr=40, na=72):
+        m = np.empty((height, width // 2 + 1), np.uint16)
+        c = np.empty(na * nr, np.int32)
+        self._check(lib.phd_debug_bin_map(self._h, width, height, nr, na, m.ctypes.data_as(C.c_void_p),
+                                          c.ctypes.data_as(C.c_void_p)))
+        return m, c.reshape(na, nr)
+
+    def debug_power_spectrum(self, rgb: np.ndarray) -> np.ndarray:
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        H, W, _ = rgb.shape
+        out = np.empty((H, W // 2 + 1), np.float32)
+        self._check(lib.phd_debug_power_spectrum(self._h, rgb.ctypes.data_as(C.c_void_p), W, H,
+                                                 out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def debug_group_counts(self, rgb: np.ndarray, params: phd_params) -> np.ndarray:
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        H, W, _ = rgb.shape
+        T = params.h_partitions * params.s_partitions * params.v_partitions + params.v_partitions + 1
+        out = np.empty(T, np.int32)
+        self._check(lib.phd_debug_group_counts(self._h, rgb.ctypes.data_as(C.c_void_p), W, H, C.byref(params),
+                                               out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+def _as_image_batch(images):
+    """-> (pointer, n, H, W, stride_bytes, keepalive)"""
+    if isinstance(images, np.ndarray):
+        a = images
+        if a.ndim == 3:
+            a = a[None]
+        if a.ndim != 4 or a.shape[3] != 3 or a.dtype != np.uint8:
+            raise ValueError("images must be uint8 [n,H,W,3]")
+        a = np.ascontiguousarray(a)
+        n, H, W, _ = a.shape
+        return a.ctypes.data_as(C.c_void_p), n, H, W, H * W * 3, a
+    # torch tensor (imported lazily: torch is plumbing for device memory only)
+    import torch
+    if isinstance(images, torch.Tensor):
+        t = images
+        if t.dim() == 3:
+            t = t[None]
+        if t.dim() != 4 or t.shape[3] != 3 or t.dtype != torch.uint8:
+            raise ValueError("images must be uint8 [n,H,W,3]")
+        t = t.contiguous()
+        n, H, W, _ = t.shape
+        return C.c_void_p(t.data_ptr()), n, H, W, H * W * 3, t
+    raise TypeError(f"unsupported image container {type(images)!r}")

@@ -1,0 +1,207 @@
+// Palette parent selection and merge plan, one CTA per image, entirely on the device so a batch
+// needs no host round trip.
+//
+// Replaces find_valid_octree_parents (src/color_quantization.c:174-203) with saliency :588-595,
+// compare_quantities :601-611 and custom_sort (src/utilities.c:132-153), and the decision part of
+// group_irregular_pixels (src/color_quantization.c:342-479) with get_node_distance_heuristic
+// :253-288.  The comparator is not a total order (float difference truncated to int, x86
+// cvttss2si overflow -> INT_MIN), so the reference's insertion sort is reproduced step by step
+// rather than replaced by "a sort".  The tie path follows the behaviour of the shipped -O0
+// binary: the first tied parent always wins (get_distance_pixel_to_parent has no return value,
+// :303-311) and pixels beyond the tail node's free room are dropped except the last (:435-440).
+#include "phd_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int trunc_f2i_x86(float d) {
+    if (!(d > -2147483904.0f && d < 2147483648.0f)) return INT_MIN;
+    return (int)d;
+}
+
+__device__ double centre_dist(const double* gh, const double* gs, const double* gv, int T, int vp, int a, int p) {
+    const int gray_start = T - (vp + 1), black = T - 1;
+    if (a < gray_start && p < gray_start) {
+        double hd = fabs(__dsub_rn(gh[a], gh[p]));
+        if (hd > 180.0) hd = __dsub_rn(360.0, hd);
+        hd = __dmul_rn(hd, (1.0) / (360.0));
+        const double sd = __dsub_rn(gs[a], gs[p]), vd = __dsub_rn(gv[a], gv[p]);
+        return __dadd_rn(__dadd_rn(__dmul_rn(hd, hd), __dmul_rn(sd, sd)), __dmul_rn(vd, vd));
+    }
+    if ((gray_start <= a && a < black && p < gray_start) || (gray_start <= p && p < black && a < gray_start)) {
+        const double sd = __dsub_rn(gs[a], gs[p]), vd = __dsub_rn(gv[a], gv[p]);
+        return __dadd_rn(__dmul_rn(sd, sd), __dmul_rn(vd, vd));
+    }
+    const double vd = __dsub_rn(gv[a], gv[p]);
+    return __dmul_rn(vd, vd);
+}
+
+__global__ void __launch_bounds__(256) k_palette_select(DevParams P, const double* __restrict__ centres,
+                                                        const float* __restrict__ sv_f,
+                                                        const u32* __restrict__ hist,
+                                                        const u16* __restrict__ counts_chunk,
+                                                        GroupPlan* __restrict__ plan_g, int* __restrict__ pal_n,
+                                                        int* __restrict__ parent_ids, int* __restrict__ tie_list,
+                                                        int* __restrict__ tie_n, int* __restrict__ tie_groups,
+                                                        long long* __restrict__ dropped) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = P.T, tid = threadIdx.x, img = blockIdx.x;
+    int* n = reinterpret_cast<int*>(smem_raw);       // [T] pixel counts
+    float* sal = reinterpret_cast<float*>(n + T);    // [T]
+    int* ids = reinterpret_cast<int*>(sal + T);      // [T] sorted group ids (parents first)
+    int* slot = ids + T;                             // [T] group -> parent slot or -1
+    int* first = slot + T;                           // [T] nearest parent slot (first of the tied ones)
+    int* nmin = first + T;                           // [T] number of equally near parents
+    int* fill = nmin + T;                            // [T] per parent slot: occupancy of its tail node
+    int* pend = fill + T;                            // [T] per parent slot: group whose last pixel is pending
+    int* take = pend + T;                            // [T] tie groups: pixels accepted from the front
+    int* keep = take + T;                            // [T] tie groups: last pixel survives
+    __shared__ int sh_N, sh_nt;
+
+    const double* gh = centres;
+    const double* gs = centres + T;
+    const double* gv = centres + 2 * T;
+    const u32* h = hist + (size_t)img * T;
+
+    for (int g = tid; g < T; g += blockDim.x) {
+        const int c = (int)h[g];
+        n[g] = c;
+        // saliency, float arithmetic in source order (:588-595)
+        const float w = __fadd_rn(P.qw, __fmul_rn(P.svw, sv_f[g]));
+        sal[g] = __fmul_rn(__fmul_rn((float)c, w), 1000.0f);
+        ids[g] = g;
+        slot[g] = -1;
+        take[g] = 0;
+        keep[g] = 0;
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        // insertion sort exactly as custom_sort walks it
+        for (int i = 1; i < T; i++) {
+            for (int j = i; j > 0; j--) {
+                const int a = ids[j], b = ids[j - 1];
+                if (trunc_f2i_x86(__fsub_rn(sal[b], sal[a])) < 0) {
+                    ids[j] = b;
+                    ids[j - 1] = a;
+                } else
+                    break;
+            }
+        }
+        int goal = (int)((double)P.hpx * P.coverage);
+        int N = 0;
+        for (int i = 0; i < T; i++) {
+            goal -= n[ids[i]];
+            if (goal <= 0) { N = i + 1; break; }
+        }
+        // coverage_thresh > 1 never reaches the goal in the reference (it then reads an unset array);
+        // every group becomes a parent here instead.
+        if (N == 0) N = T;
+        sh_N = N;
+        for (int j = 0; j < N; j++) {
+            slot[ids[j]] = j;
+            const int pn = n[ids[j]];
+            fill[j] = pn > 0 ? ((pn - 1) % P.L) + 1 : 0;
+            pend[j] = -1;
+        }
+    }
+    __syncthreads();
+    const int N = sh_N;
+
+    // nearest parent(s) of every non-empty non-parent group
+    for (int g = tid; g < T; g += blockDim.x) {
+        first[g] = -1;
+        nmin[g] = 0;
+        if (n[g] == 0 || slot[g] >= 0) continue;
+        double m = (double)T * (double)T;
+        int cnt = 0, fi = -1;
+        for (int j = 0; j < N; j++) {
+            const double d = centre_dist(gh, gs, gv, T, P.vp, g, ids[j]);
+            if (d < m) { m = d; cnt = 1; fi = j; }
+            else if (d == m) cnt++;
+        }
+        first[g] = fi;
+        nmin[g] = cnt;
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        int ties = 0, nt = 0;
+        long long drop = 0;
+        for (int g = 0; g < T; g++) {
+            if (n[g] == 0 || slot[g] >= 0 || first[g] < 0) continue;
+            const int f = first[g];
+            if (nmin[g] > 1) {
+                ties++;
+                const int room = P.L - fill[f];
+                const int tk = room < n[g] ? room : n[g];
+                take[g] = tk;
+                fill[f] += tk;
+                if (tk < n[g]) {
+                    if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; }
+                    pend[f] = g;
+                    keep[g] = 1;
+                    drop += n[g] - tk - 1;
+                }
+                tie_list[(size_t)img * T + nt++] = g;
+            } else {
+                take[g] = -1;
+                if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; pend[f] = -1; }
+                fill[f] = ((n[g] - 1) % P.L) + 1;
+            }
+        }
+        sh_nt = nt;
+        pal_n[img] = N;
+        tie_n[img] = nt;
+        tie_groups[img] = ties;
+        dropped[img] = drop;
+    }
+    __syncthreads();
+
+    // write the plan; tie groups locate their partial / last chunk from the per-chunk counts
+    for (int g = tid; g < T; g += blockDim.x) {
+        GroupPlan gp;
+        gp.slot = -1; gp.mode = 0; gp.cstar = -1; gp.need = 0; gp.clast = -1;
+        if (slot[g] >= 0) { gp.slot = (short)slot[g]; gp.mode = 1; }
+        else if (n[g] > 0 && first[g] >= 0) {
+            gp.slot = (short)first[g];
+            if (take[g] < 0) gp.mode = 1;
+            else {
+                gp.mode = 2;
+                const u16* cc = counts_chunk + (size_t)img * P.nchunks * T + g;
+                const int tk = take[g];
+                int cum = 0, cstar = -1, need = 0, clast = -1;
+                bool found = (tk == 0);
+                for (int c = 0; c < P.nchunks; c++) {
+                    const int k = cc[(size_t)c * T];
+                    if (k == 0) continue;
+                    clast = c;
+                    if (!found) {
+                        if (cum + k >= tk) { cstar = c; need = tk - cum; found = true; }
+                        cum += k;
+                    }
+                }
+                if (tk >= n[g]) { cstar = P.nchunks; need = 0; }  // everything fits: accept all chunks
+                gp.cstar = cstar;
+                gp.need = need;
+                gp.clast = keep[g] ? clast : -1;
+            }
+        }
+        plan_g[(size_t)img * T + g] = gp;
+    }
+    for (int j = tid; j < T; j += blockDim.x) parent_ids[(size_t)img * T + j] = j < N ? ids[j] : -1;
+}
+
+}  // namespace
+
+void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
+                               cudaStream_t st, int* launches) {
+    const size_t smem = (size_t)P.T * 10 * sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_palette_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.hist, ws.counts_chunk, ws.plan, ws.pal_n,
+                                              ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped);
+    *launches += 1;
+}

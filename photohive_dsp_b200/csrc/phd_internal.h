@@ -1,0 +1,124 @@
+// Internal declarations shared by the CUDA translation units of libreport_data.so.
+// Nothing here is part of the C ABI (include/photohive_dsp.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "photohive_dsp.h"
+
+#define PHD_CHUNK 4096        // HSV pixels per front-end chunk (one CTA iteration)
+#define PHD_FE_THREADS 256    // front-end CTA size; each thread owns PHD_CHUNK/PHD_FE_THREADS consecutive pixels
+#define PHD_PX_PER_THREAD (PHD_CHUNK / PHD_FE_THREADS)
+#define PHD_MAX_GROUPS 2048   // T = h*s*v + v + 1 upper bound (shared-memory tables)
+#define PHD_MAX_BINS 8192     // na*nr upper bound
+#define PHD_MAX_FACTORS 24
+
+// Fixed-point scales of the integer accumulators (all sums are exact integers => order independent).
+#define PHD_S_SHIFT 30        // saturation: s * 2^30
+#define PHD_T_SHIFT 21        // wrapped hue: t * 2^21 (t <= 360)
+#define PHD_LN_SHIFT 20       // ln(power): value * 2^20 (value < 2^6)
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+
+// Everything a kernel needs to know about the job; passed by value.
+struct DevParams {
+    int W, H, fw;        // full image, fw = W/2+1 spectrum columns
+    int dw, dh, ds;      // HSV (possibly downsampled) image and the rate
+    long long npx, hpx;  // W*H and dw*dh
+    int nchunks;         // ceil(hpx / PHD_CHUNK)
+    int hp, sp, vp, T;
+    double Lh, Ls, Lv, bt, gt;
+    double coverage;
+    int L;               // linked_list_size
+    float qw, svw;
+    int nr, na, nbins;
+    double streak, magthr;
+    int denom;
+    int max_boxes;
+    size_t image_stride;
+    int aligned16;       // image base and stride are 16-byte aligned
+};
+
+// Per-group merge plan written by the palette-select kernel, read by palette-accumulate.
+struct GroupPlan {
+    short slot;   // parent slot this group's pixels are summed into (-1: none)
+    short mode;   // 0 none, 1 every pixel, 2 tie (partial, see below)
+    int cstar;    // tie: chunks < cstar fully accepted, chunk == cstar accepts the first `need` pixels
+    int need;
+    int clast;    // tie: chunk holding the group's last pixel when that pixel alone survives, else -1
+};
+
+// Per-parent integer accumulators (palette-accumulate -> finalize).
+struct SlotAcc {
+    u64 cnt, summax, n255, s_sum, t_sum;
+};
+
+// Per-image scalar accumulators of the front end.
+struct ImageAcc {
+    u64 sum[3];    // sum of k per channel
+    u64 sumsq[3];  // sum of k^2 per channel
+    u64 s_sum;     // sum of s * 2^30 over the HSV image
+    u64 pad;
+};
+
+struct SharpAcc {
+    long long s1;  // sum f        (f = integer Laplacian of the gray numerator)
+    u64 s2lo, s2hi; // sum f^2 split as 32-bit halves
+    u64 pad;
+};
+
+struct FftPlan {
+    int n;
+    int nfac;
+    int fac[PHD_MAX_FACTORS];
+    const float2* tw;  // device, n entries exp(-2 pi i k / n)
+};
+
+// Device workspace for one sub-batch.
+struct Workspace {
+    int capacity;  // images
+    u16* counts_chunk;   // [cap][nchunks][T]
+    u32* hist;           // [cap][T]
+    ImageAcc* iacc;      // [cap]
+    GroupPlan* plan;     // [cap][T]
+    int* pal_n;          // [cap]
+    int* parent_ids;     // [cap][T]
+    int* tie_list;       // [cap][T]
+    int* tie_n;          // [cap]
+    int* tie_groups;     // [cap]
+    long long* dropped;  // [cap]
+    SlotAcc* sacc;       // [cap][T]
+    float2* spec;        // [cap][H][fw]
+    u64* binsum;         // [cap][nbins]
+    u32* maxpow;         // [cap] float bits
+    SharpAcc* sharp;     // [cap][max_boxes]
+    int* boxes;          // [cap][max_boxes][4]
+};
+
+// ---- launchers (each in its own .cu) --------------------------------------------------------
+void phd_launch_frontend(const uint8_t* rgb, const DevParams& P, int nimg, const double* centres, Workspace& ws,
+                         cudaStream_t st, int* launches);
+void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
+                               cudaStream_t st, int* launches);
+void phd_launch_palette_accumulate(const uint8_t* rgb, const DevParams& P, int nimg, const double* centres,
+                                   Workspace& ws, cudaStream_t st, int* launches);
+void phd_launch_group_sweep(const DevParams& P, u16* out_dev, cudaStream_t st);
+
+int phd_fft_plan_factors(int n, int* fac, int* nfac);  // 0 ok, nonzero unsupported
+void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st);
+int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* spec,
+                        cudaStream_t st, int* launches);
+int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* spec, const u16* binmap,
+                             Workspace& ws, float* power_out, cudaStream_t st, int* launches);
+void phd_launch_bin_map(int W, int H, int nr, int na, u16* map_dev, int* counts_dev, cudaStream_t st);
+
+void phd_launch_sharpness(const uint8_t* rgb, const DevParams& P, int nimg, int max_w, int max_h, Workspace& ws,
+                          cudaStream_t st, int* launches);
+void phd_launch_finalize(const DevParams& P, int nimg, const double* centres, const int* bincount, Workspace& ws,
+                         const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches);
+
+size_t phd_fft_cols_smem(const DevParams& P, int* tile_cols);

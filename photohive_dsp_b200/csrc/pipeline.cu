@@ -1,0 +1,855 @@
+// Host side of libreport_data.so: the C ABI of include/photohive_dsp.h.
+//
+// Part 1 mirrors src/interface.c:20-111 (get_full_report_data / free_full_report) and
+// src/blur_profile.c:140-180 (get_blur_profile_visual); the stage ORDER of interface.c:28-93 is kept as a
+// sequence of kernels on one stream.  Part 2 is the batch interface.  There is no CPU implementation of
+// any stage in this file: without a CUDA device every entry point fails loudly.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "phd_internal.h"
+
+namespace {
+
+struct ShapePlan {
+    int W, H, nr, na;
+    FftPlan row, col;
+    float2* tw_row = nullptr;
+    float2* tw_col = nullptr;
+    u16* binmap = nullptr;
+    int* bincount = nullptr;
+};
+
+struct ParamTables {
+    phd_params p;
+    double* centres = nullptr;  // device [3*T]: group centre h, s, v
+    float* sv_f = nullptr;      // device [T]: (float)(s*v) of the centre
+};
+
+}  // namespace
+
+struct phd_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::vector<ShapePlan> shapes;
+    std::vector<ParamTables> tables;
+    Workspace ws{};
+    unsigned char* ws_zero = nullptr;  // one allocation holding every accumulator that must start at zero
+    size_t ws_zero_bytes = 0;
+    size_t ws_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned char* d_rgb = nullptr;
+    size_t d_rgb_bytes = 0;
+    unsigned char* d_records = nullptr;
+    size_t d_records_bytes = 0;
+    std::vector<cudaEvent_t> events;
+    float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int last_launches = 0;
+    char err[512] = {0};
+};
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                                               \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            snprintf((ctx)->err, sizeof((ctx)->err), "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), \
+                     __FILE__, __LINE__, #expr);                                                          \
+            fprintf(stderr, "photohive_dsp: %s\n", (ctx)->err);                                           \
+            return PHD_E_CUDA;                                                                            \
+        }                                                                                                 \
+    } while (0)
+
+int fail(phd_context* ctx, int code, const char* msg) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    fprintf(stderr, "photohive_dsp: %s\n", msg);
+    return code;
+}
+
+// src/utilities.c:64-87 (limits :11-13)
+bool reference_rejects(int width, int height, char* why, size_t n) {
+    if (height < 350 || width < 350) {
+        snprintf(why, n, "Error: Image height and width must be greater than 350. Height: %d\tWidth%d", height, width);
+        return true;
+    }
+    if ((long long)height * width > 12000LL * 10000LL) {
+        snprintf(why, n, "Error: Image must have less than %d pixels.", 12000 * 10000);
+        return true;
+    }
+    const float aspect = (float)height / (float)width;
+    if (aspect < (1.0 / 5.0) || aspect > (5.0 / 1.0)) {
+        snprintf(why, n, "Error: Invalid aspect ratio: %f", aspect);
+        return true;
+    }
+    return false;
+}
+
+bool same_params_for_tables(const phd_params& a, const phd_params& b) {
+    return a.h_partitions == b.h_partitions && a.s_partitions == b.s_partitions &&
+           a.v_partitions == b.v_partitions && a.black_thresh == b.black_thresh && a.gray_thresh == b.gray_thresh;
+}
+
+int check_params(phd_context* ctx, const phd_params* p, int max_boxes) {
+    if (!p) return fail(ctx, PHD_E_BAD_PARAMS, "params pointer is NULL");
+    if (p->h_partitions <= 0 || p->s_partitions <= 0 || p->v_partitions <= 0)
+        return fail(ctx, PHD_E_BAD_PARAMS, "ERROR: h_partitions, s_partitions and v_partitions must be nonzero");
+    const long long T = (long long)p->h_partitions * p->s_partitions * p->v_partitions + p->v_partitions + 1;
+    if (T > PHD_MAX_GROUPS) return fail(ctx, PHD_E_BAD_PARAMS, "palette grid larger than PHD_MAX_GROUPS groups");
+    if (p->h_partitions > 360) return fail(ctx, PHD_E_BAD_PARAMS, "h_partitions > 360 gives a zero-width hue bin");
+    if (p->radius_partitions <= 0 || p->angle_partitions <= 1 ||
+        (long long)p->radius_partitions * p->angle_partitions > PHD_MAX_BINS || p->angle_partitions > 180)
+        return fail(ctx, PHD_E_BAD_PARAMS, "radius/angle partitions out of range");
+    if (p->linked_list_size <= 0) return fail(ctx, PHD_E_BAD_PARAMS, "linked_list_size must be positive");
+    if (p->blur_cutoff_ratio_denom <= 0) return fail(ctx, PHD_E_BAD_PARAMS, "blur_cutoff_ratio_denom must be positive");
+    if (max_boxes < 0) return fail(ctx, PHD_E_BAD_PARAMS, "negative box count");
+    return PHD_OK;
+}
+
+void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_boxes, size_t stride, int aligned16) {
+    memset(&P, 0, sizeof(P));
+    P.W = W; P.H = H; P.fw = W / 2 + 1;
+    P.ds = p.downsample_rate > 1 ? p.downsample_rate : 1;
+    P.dw = P.ds > 1 ? W / P.ds : W;
+    P.dh = P.ds > 1 ? H / P.ds : H;
+    P.npx = (long long)W * H;
+    P.hpx = (long long)P.dw * P.dh;
+    P.nchunks = (int)((P.hpx + PHD_CHUNK - 1) / PHD_CHUNK);
+    P.hp = p.h_partitions; P.sp = p.s_partitions; P.vp = p.v_partitions;
+    P.T = P.hp * P.sp * P.vp + P.vp + 1;
+    // src/color_quantization.c:41-45
+    P.Lh = (double)(360 / P.hp);
+    P.Ls = (1 - p.gray_thresh) / P.sp;
+    P.Lv = (1 - p.black_thresh) / P.vp;
+    P.bt = p.black_thresh; P.gt = p.gray_thresh;
+    P.coverage = p.coverage_thresh;
+    P.L = p.linked_list_size;
+    P.qw = p.quantity_weight; P.svw = p.saturation_value_weight;
+    P.nr = p.radius_partitions; P.na = p.angle_partitions; P.nbins = P.nr * P.na;
+    P.streak = p.fft_streak_thresh; P.magthr = p.magnitude_thresh; P.denom = p.blur_cutoff_ratio_denom;
+    P.max_boxes = max_boxes;
+    P.image_stride = stride;
+    P.aligned16 = aligned16;
+}
+
+// Group centres exactly as initialize_octree computes them (src/color_quantization.c:58-98); host doubles, no FMA.
+int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
+    for (auto& t : ctx->tables)
+        if (same_params_for_tables(t.p, p)) { *out = &t; return PHD_OK; }
+    const int hp = p.h_partitions, sp = p.s_partitions, vp = p.v_partitions;
+    const int T = hp * sp * vp + vp + 1;
+    std::vector<double> c(3 * (size_t)T, 0.0);
+    std::vector<float> sv(T, 0.f);
+    double* gh = c.data();
+    double* gs = gh + T;
+    double* gv = gs + T;
+    volatile double Lh = (double)(360 / hp);
+    volatile double Ls = (1 - p.gray_thresh) / sp;
+    volatile double Lv = (1 - p.black_thresh) / vp;
+    volatile double half_h = Lh / 2, s_offs = Ls / 2 + p.gray_thresh, v_offs = Lv / 2 + p.black_thresh;
+    int i = 0;
+    for (int h = 0; h < hp; h++)
+        for (int s = 0; s < sp; s++)
+            for (int v = 0; v < vp; v++) {
+                i = (h * sp + s) * vp + v;
+                volatile double a = h * Lh, b = s * Ls, d = v * Lv;  // products rounded before the add
+                gh[i] = a + half_h;
+                gs[i] = b + s_offs;
+                gv[i] = d + v_offs;
+            }
+    volatile double L_gray = (1.0f - p.black_thresh) / (double)vp;
+    for (int j = 0; j < vp; j++) {
+        i++;
+        volatile double a = L_gray * j;
+        gh[i] = 0; gs[i] = 0; gv[i] = a + v_offs;
+    }
+    i++;
+    gh[i] = gs[i] = gv[i] = 0;
+    for (int g = 0; g < T; g++) {
+        volatile double prod = gs[g] * gv[g];
+        sv[g] = (float)prod;
+    }
+    ParamTables t;
+    t.p = p;
+    CUDA_TRY(ctx, cudaMalloc(&t.centres, sizeof(double) * 3 * T));
+    CUDA_TRY(ctx, cudaMalloc(&t.sv_f, sizeof(float) * T));
+    CUDA_TRY(ctx, cudaMemcpyAsync(t.centres, c.data(), sizeof(double) * 3 * T, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(t.sv_f, sv.data(), sizeof(float) * T, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->tables.push_back(t);
+    *out = &ctx->tables.back();
+    return PHD_OK;
+}
+
+int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
+    for (auto& s : ctx->shapes)
+        if (s.W == W && s.H == H && s.nr == nr && s.na == na) { *out = &s; return PHD_OK; }
+    ShapePlan s;
+    s.W = W; s.H = H; s.nr = nr; s.na = na;
+    s.row.n = W; s.col.n = H;
+    if (phd_fft_plan_factors(W, s.row.fac, &s.row.nfac) || phd_fft_plan_factors(H, s.col.fac, &s.col.nfac))
+        return fail(ctx, PHD_E_UNSUPPORTED, "image side has a prime factor > 31: FFT length not supported by this build");
+    const size_t nspec = (size_t)(W / 2 + 1) * H;
+    CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * W));
+    CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * H));
+    CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
+    CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
+    phd_fill_twiddles(s.tw_row, W, ctx->stream);
+    phd_fill_twiddles(s.tw_col, H, ctx->stream);
+    phd_launch_bin_map(W, H, nr, na, s.binmap, s.bincount, ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    s.row.tw = s.tw_row;
+    s.col.tw = s.tw_col;
+    ctx->shapes.push_back(s);
+    *out = &ctx->shapes.back();
+    return PHD_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int ensure_workspace(phd_context* ctx, const DevParams& P, int cap) {
+    const size_t key[8] = {(size_t)cap, (size_t)P.T, (size_t)P.nchunks, (size_t)P.H, (size_t)P.fw,
+                           (size_t)P.nbins, (size_t)P.max_boxes, 0};
+    if (memcmp(key, ctx->ws_key, sizeof(key)) == 0 && ctx->ws.capacity == cap) return PHD_OK;
+    Workspace& w = ctx->ws;
+    cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
+    cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
+    cudaFree(ctx->ws_zero);
+    memset(&w, 0, sizeof(w));
+    ctx->ws_zero = nullptr;
+    const size_t T = P.T, c = cap;
+    CUDA_TRY(ctx, cudaMalloc(&w.counts_chunk, sizeof(u16) * c * P.nchunks * T));
+    CUDA_TRY(ctx, cudaMalloc(&w.plan, sizeof(GroupPlan) * c * T));
+    CUDA_TRY(ctx, cudaMalloc(&w.pal_n, sizeof(int) * c));
+    CUDA_TRY(ctx, cudaMalloc(&w.parent_ids, sizeof(int) * c * T));
+    CUDA_TRY(ctx, cudaMalloc(&w.tie_list, sizeof(int) * c * T));
+    CUDA_TRY(ctx, cudaMalloc(&w.tie_n, sizeof(int) * c));
+    CUDA_TRY(ctx, cudaMalloc(&w.tie_groups, sizeof(int) * c));
+    CUDA_TRY(ctx, cudaMalloc(&w.dropped, sizeof(long long) * c));
+    CUDA_TRY(ctx, cudaMalloc(&w.spec, sizeof(float2) * c * P.H * P.fw));
+    CUDA_TRY(ctx, cudaMalloc(&w.boxes, sizeof(int) * 4 * c * (P.max_boxes > 0 ? P.max_boxes : 1)));
+    // zero-initialised accumulators, contiguous so one memset per sub-batch clears them
+    size_t off = 0;
+    const size_t o_hist = off; off = align_up(off + sizeof(u32) * c * T, 256);
+    const size_t o_iacc = off; off = align_up(off + sizeof(ImageAcc) * c, 256);
+    const size_t o_sacc = off; off = align_up(off + sizeof(SlotAcc) * c * T, 256);
+    const size_t o_bins = off; off = align_up(off + sizeof(u64) * c * P.nbins, 256);
+    const size_t o_maxp = off; off = align_up(off + sizeof(u32) * c, 256);
+    const size_t o_sharp = off; off = align_up(off + sizeof(SharpAcc) * c * (P.max_boxes > 0 ? P.max_boxes : 1), 256);
+    CUDA_TRY(ctx, cudaMalloc(&ctx->ws_zero, off));
+    ctx->ws_zero_bytes = off;
+    w.hist = reinterpret_cast<u32*>(ctx->ws_zero + o_hist);
+    w.iacc = reinterpret_cast<ImageAcc*>(ctx->ws_zero + o_iacc);
+    w.sacc = reinterpret_cast<SlotAcc*>(ctx->ws_zero + o_sacc);
+    w.binsum = reinterpret_cast<u64*>(ctx->ws_zero + o_bins);
+    w.maxpow = reinterpret_cast<u32*>(ctx->ws_zero + o_maxp);
+    w.sharp = reinterpret_cast<SharpAcc*>(ctx->ws_zero + o_sharp);
+    w.capacity = cap;
+    memcpy(ctx->ws_key, key, sizeof(key));
+    return PHD_OK;
+}
+
+int ensure_bytes(phd_context* ctx, unsigned char** buf, size_t* have, size_t need) {
+    if (*have >= need) return PHD_OK;
+    cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    CUDA_TRY(ctx, cudaMalloc(buf, need));
+    *have = need;
+    return PHD_OK;
+}
+
+bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int pick_sub_batch(const DevParams& P, int n_images) {
+    const char* env = getenv("PHD_SUB_BATCH");
+    long long sub = 0;
+    if (env) sub = atoll(env);
+    if (sub <= 0) {
+        // keep the row-transformed spectra of one sub-batch around 128 MB (L2 is 126 MB on B200)
+        const double per = (double)P.H * P.fw * sizeof(float2);
+        sub = (long long)(128.0 * 1024 * 1024 / per);
+        if (sub < 1) sub = 1;
+        if (sub > 64) sub = 64;
+    }
+    if (sub > n_images) sub = n_images;
+    return (int)sub;
+}
+
+enum { ST_FRONT = 1, ST_SELECT, ST_ACCUM, ST_ROWS, ST_COLS, ST_SHARP, ST_FINAL };
+
+// The pipeline on device-resident input.  records_dev: device buffer for n_images records.
+int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on_device, int n_images, int W, int H,
+                 size_t image_stride, const int* boxes_host, int max_boxes, const phd_params& p,
+                 unsigned char* records_dev, const phd_flat_layout& lay) {
+    DevParams P;
+    const size_t tight = (size_t)W * H * 3;
+    const size_t dev_stride = input_on_device ? image_stride : align_up(tight, 16);
+    int aligned16 = 1;
+    if (input_on_device) aligned16 = (((uintptr_t)rgb_host_or_dev % 16) == 0 && image_stride % 16 == 0) ? 1 : 0;
+    fill_dev_params(P, p, W, H, max_boxes, dev_stride, aligned16);
+    if (P.dw < 1 || P.dh < 1) return fail(ctx, PHD_E_BAD_PARAMS, "downsample_rate leaves no pixels");
+
+    ShapePlan* shape;
+    ParamTables* tab;
+    int rc;
+    if ((rc = get_shape(ctx, W, H, P.nr, P.na, &shape)) != PHD_OK) return rc;
+    if ((rc = get_tables(ctx, p, &tab)) != PHD_OK) return rc;
+    const int sub = pick_sub_batch(P, n_images);
+    if ((rc = ensure_workspace(ctx, P, sub)) != PHD_OK) return rc;
+    if (!input_on_device && (rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, dev_stride * sub)) != PHD_OK) return rc;
+    int tc;
+    if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
+        return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
+
+    cudaStream_t st = ctx->stream;
+    const int nsub = (n_images + sub - 1) / sub;
+    const size_t nev = 2 + (size_t)nsub * 8;
+    while (ctx->events.size() < nev) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreate(&e));
+        ctx->events.push_back(e);
+    }
+    int launches = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->events[0], st));
+    for (int sb = 0; sb < nsub; sb++) {
+        const int first = sb * sub;
+        const int n = (n_images - first < sub) ? (n_images - first) : sub;
+        const uint8_t* d_in;
+        if (input_on_device) d_in = rgb_host_or_dev + (size_t)first * image_stride;
+        else {
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_rgb, dev_stride, rgb_host_or_dev + (size_t)first * image_stride,
+                                            image_stride, tight, n, cudaMemcpyHostToDevice, st));
+            d_in = ctx->d_rgb;
+        }
+        int max_w = 0, max_h = 0;
+        if (max_boxes > 0) {
+            const int* b = boxes_host + (size_t)first * max_boxes * 4;
+            for (int i = 0; i < n * max_boxes; i++) {
+                const int w = b[4 * i + 3] - b[4 * i + 2], h = b[4 * i + 1] - b[4 * i];
+                if (w > max_w) max_w = w;
+                if (h > max_h) max_h = h;
+            }
+            if (max_w > W) max_w = W;
+            if (max_h > H) max_h = H;
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.boxes, b, sizeof(int) * 4 * (size_t)n * max_boxes,
+                                          cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
+        cudaEvent_t* ev = &ctx->events[2 + (size_t)sb * 8];
+        CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
+        phd_launch_frontend(d_in, P, n, tab->centres, ctx->ws, st, &launches);
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_FRONT], st));
+        phd_launch_palette_select(P, n, tab->centres, tab->sv_f, ctx->ws, st, &launches);
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_SELECT], st));
+        phd_launch_palette_accumulate(d_in, P, n, tab->centres, ctx->ws, st, &launches);
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_ACCUM], st));
+        if (phd_launch_fft_rows(d_in, P, n, shape->row, ctx->ws.spec, st, &launches))
+            return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_ROWS], st));
+        if (phd_launch_fft_cols_blur(P, n, shape->col, ctx->ws.spec, shape->binmap, ctx->ws, nullptr, st, &launches))
+            return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_COLS], st));
+        phd_launch_sharpness(d_in, P, n, max_w, max_h, ctx->ws, st, &launches);
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_SHARP], st));
+        phd_launch_finalize(P, n, tab->centres, shape->bincount, ctx->ws, lay,
+                            records_dev + (size_t)first * lay.record_bytes, st, &launches);
+        CUDA_TRY(ctx, cudaEventRecord(ev[ST_FINAL], st));
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->events[1], st));
+    ctx->last_launches = launches;
+    return PHD_OK;
+}
+
+int collect_timing(phd_context* ctx, int nsub) {
+    for (int i = 0; i < 8; i++) ctx->last_ms[i] = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[0], ctx->events[0], ctx->events[1]));
+    for (int sb = 0; sb < nsub; sb++) {
+        cudaEvent_t* ev = &ctx->events[2 + (size_t)sb * 8];
+        for (int s = 1; s <= 7; s++) {
+            float ms = 0.f;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev[s - 1], ev[s]));
+            ctx->last_ms[s] += ms;
+        }
+    }
+    return PHD_OK;
+}
+
+// Image_RGB planes (doubles k/255.0) -> packed 8-bit, with an exactness flag.
+__global__ void k_ingest_f64(const double* __restrict__ r, const double* __restrict__ g, const double* __restrict__ b,
+                             long long npx, uint8_t* __restrict__ out, int* __restrict__ not_8bit) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npx) return;
+    const double v[3] = {r[i], g[i], b[i]};
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        int k = (int)(v[c] * 255.0 + 0.5);
+        k = min(max(k, 0), 255);
+        if (__ddiv_rn((double)k, 255.0) != v[c]) bad = true;
+        out[3 * i + c] = (uint8_t)k;
+    }
+    if (bad) atomicOr(not_8bit, 1);
+}
+
+std::mutex g_default_mu;
+phd_context* g_default_ctx = nullptr;
+
+phd_context* default_context() {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx) {
+        int dev = 0;
+        const char* env = getenv("PHD_DEVICE");
+        if (env) dev = atoi(env);
+        if (phd_context_create(dev, &g_default_ctx) != PHD_OK) g_default_ctx = nullptr;
+    }
+    return g_default_ctx;
+}
+
+}  // namespace
+
+// =============================================================================================
+// Part 2: batch interface
+// =============================================================================================
+extern "C" {
+
+void phd_default_params(phd_params* p) {
+    p->h_partitions = 18; p->s_partitions = 2; p->v_partitions = 3;
+    p->black_thresh = 0.1; p->gray_thresh = 0.1; p->coverage_thresh = 0.95;
+    p->linked_list_size = 1000; p->downsample_rate = 1;
+    p->radius_partitions = 40; p->angle_partitions = 72;
+    p->quantity_weight = 0.1f; p->saturation_value_weight = 0.9f;
+    p->fft_streak_thresh = 1.20; p->magnitude_thresh = 0.3; p->blur_cutoff_ratio_denom = 2;
+}
+
+int phd_context_create(int device, phd_context** out) {
+    if (!out) return PHD_E_BAD_PARAMS;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        fprintf(stderr, "photohive_dsp: no CUDA device available; this library has no CPU path\n");
+        return PHD_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        fprintf(stderr, "photohive_dsp: device %d out of range (%d devices)\n", device, ndev);
+        return PHD_E_NO_DEVICE;
+    }
+    phd_context* ctx = new phd_context();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fprintf(stderr, "photohive_dsp: cannot initialise CUDA device %d: %s\n", device,
+                cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return PHD_E_CUDA;
+    }
+    *out = ctx;
+    return PHD_OK;
+}
+
+void phd_context_destroy(phd_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->shapes) { cudaFree(s.tw_row); cudaFree(s.tw_col); cudaFree(s.binmap); cudaFree(s.bincount); }
+    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); }
+    Workspace& w = ctx->ws;
+    cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
+    cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
+    cudaFree(ctx->ws_zero); cudaFree(ctx->d_rgb); cudaFree(ctx->d_records);
+    for (auto e : ctx->events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* phd_last_error(const phd_context* ctx) { return ctx ? ctx->err : "no context"; }
+
+int phd_flat_get_layout(const phd_params* p, int max_boxes, phd_flat_layout* out) {
+    if (!p || !out || max_boxes < 0) return PHD_E_BAD_PARAMS;
+    if (p->h_partitions <= 0 || p->s_partitions <= 0 || p->v_partitions <= 0 || p->radius_partitions <= 0 ||
+        p->angle_partitions <= 0)
+        return PHD_E_BAD_PARAMS;
+    const size_t T = (size_t)p->h_partitions * p->s_partitions * p->v_partitions + p->v_partitions + 1;
+    const size_t nb = (size_t)p->radius_partitions * p->angle_partitions;
+    size_t off = align_up(sizeof(phd_flat_head), 16);
+    out->off_palette_hsv = off; off += sizeof(double) * 3 * T;
+    out->off_palette_pct = off; off += sizeof(double) * T;
+    out->off_parent_ids = off; off = align_up(off + sizeof(int) * T, 8);
+    out->off_blur_bins = off; off += sizeof(double) * nb;
+    out->off_sharpness = off; off += sizeof(double) * (size_t)max_boxes;
+    out->record_bytes = align_up(off, 16);
+    out->T = (int)T; out->na = p->angle_partitions; out->nr = p->radius_partitions; out->max_boxes = max_boxes;
+    return PHD_OK;
+}
+
+int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_images, int width, int height,
+                       size_t image_stride, const int* boxes, int max_boxes, const phd_params* p, void* records) {
+    if (!ctx) return PHD_E_BAD_PARAMS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err[0] = 0;
+    if (!rgb || !records || n_images <= 0) return fail(ctx, PHD_E_BAD_PARAMS, "Error: Image pointer is NULL.");
+    int rc = check_params(ctx, p, max_boxes);
+    if (rc != PHD_OK) return rc;
+    if (max_boxes > 0 && !boxes) return fail(ctx, PHD_E_BAD_PARAMS, "max_boxes > 0 but boxes is NULL");
+    char why[256];
+    if (reference_rejects(width, height, why, sizeof(why))) return fail(ctx, PHD_E_REJECTED, why);
+    if (image_stride < (size_t)width * height * 3) return fail(ctx, PHD_E_BAD_PARAMS, "image_stride smaller than one image");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    phd_flat_layout lay;
+    phd_flat_get_layout(p, max_boxes, &lay);
+    const bool in_dev = is_device_pointer(rgb);
+    const bool out_dev = is_device_pointer(records);
+    unsigned char* rec_dev = (unsigned char*)records;
+    if (!out_dev) {
+        if ((rc = ensure_bytes(ctx, &ctx->d_records, &ctx->d_records_bytes, lay.record_bytes * (size_t)n_images)) != PHD_OK)
+            return rc;
+        rec_dev = ctx->d_records;
+    }
+    rc = run_pipeline(ctx, rgb, in_dev, n_images, width, height, image_stride, boxes, max_boxes, *p, rec_dev, lay);
+    if (rc != PHD_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    if (!out_dev)
+        CUDA_TRY(ctx, cudaMemcpyAsync(records, rec_dev, lay.record_bytes * (size_t)n_images, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    DevParams P;
+    fill_dev_params(P, *p, width, height, max_boxes, image_stride, 0);
+    const int sub = pick_sub_batch(P, n_images);
+    return collect_timing(ctx, (n_images + sub - 1) / sub);
+}
+
+int phd_last_timing(const phd_context* ctx, float ms[8]) {
+    if (!ctx) return 0;
+    for (int i = 0; i < 8; i++) ms[i] = ctx->last_ms[i];
+    return ctx->last_launches;
+}
+
+Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_flat_layout* lay) {
+    if (!record || !lay) return NULL;
+    const unsigned char* rec = (const unsigned char*)record;
+    const phd_flat_head* h = (const phd_flat_head*)rec;
+    if (h->status != 0) return NULL;
+    const double* hsv = (const double*)(rec + lay->off_palette_hsv);
+    const double* pct = (const double*)(rec + lay->off_palette_pct);
+    const int* pid = (const int*)(rec + lay->off_parent_ids);
+    const double* bins = (const double*)(rec + lay->off_blur_bins);
+    const double* sharp = (const double*)(rec + lay->off_sharpness);
+
+    Full_Report_Data* r = (Full_Report_Data*)malloc(sizeof(Full_Report_Data));
+    r->rgb_stats = (RGB_Statistics*)calloc(1, sizeof(RGB_Statistics));
+    r->rgb_stats->Br = h->rgb_stats[0]; r->rgb_stats->Bg = h->rgb_stats[1]; r->rgb_stats->Bb = h->rgb_stats[2];
+    r->rgb_stats->Cr = h->rgb_stats[3]; r->rgb_stats->Cg = h->rgb_stats[4]; r->rgb_stats->Cb = h->rgb_stats[5];
+    r->average_saturation = h->average_saturation;
+
+    Color_Palette* cp = (Color_Palette*)malloc(sizeof(Color_Palette));
+    cp->N = h->palette_n;
+    cp->averages = (Pixel_HSV*)calloc(cp->N > 0 ? cp->N : 1, sizeof(Pixel_HSV));
+    cp->percentages = (Pixel*)calloc(cp->N > 0 ? cp->N : 1, sizeof(Pixel));
+    for (int i = 0; i < cp->N; i++) {
+        cp->averages[i].parent_id = pid[i];
+        cp->averages[i].h = hsv[3 * i]; cp->averages[i].s = hsv[3 * i + 1]; cp->averages[i].v = hsv[3 * i + 2];
+        cp->percentages[i] = pct[i];
+    }
+    r->color_palette = cp;
+
+    Blur_Profile* bp = (Blur_Profile*)malloc(sizeof(Blur_Profile));
+    bp->num_angle_bins = h->num_angle_bins; bp->num_radius_bins = h->num_radius_bins;
+    bp->angle_bin_size = h->angle_bin_size; bp->radius_bin_size = h->radius_bin_size;
+    bp->bins = (Bin**)malloc(sizeof(Bin*) * bp->num_angle_bins);
+    for (int a = 0; a < bp->num_angle_bins; a++) {
+        bp->bins[a] = (Bin*)malloc(sizeof(Bin) * bp->num_radius_bins);
+        memcpy(bp->bins[a], bins + (size_t)a * bp->num_radius_bins, sizeof(Bin) * bp->num_radius_bins);
+    }
+    r->blur_profile = bp;
+
+    Blur_Vector_Group* bv = (Blur_Vector_Group*)calloc(1, sizeof(Blur_Vector_Group));
+    bv->len_vectors = 10;
+    bv->blur_vectors = (Blur_Vector*)calloc(10, sizeof(Blur_Vector));
+    for (int k = 0; k < 10; k++) { bv->blur_vectors[k].angle = h->blur_vec_angle[k]; bv->blur_vectors[k].magnitude = h->blur_vec_mag[k]; }
+    r->blur_vectors = bv;
+
+    r->sharpness = NULL;
+    if (h->n_sharpness >= 0) {
+        Sharpnesses* s = (Sharpnesses*)malloc(sizeof(Sharpnesses));
+        s->N = h->n_sharpness;
+        s->sharpness = (Pixel*)calloc(s->N > 0 ? s->N : 1, sizeof(Pixel));
+        for (int i = 0; i < s->N; i++) s->sharpness[i] = sharp[i];
+        r->sharpness = s;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test hooks
+// ---------------------------------------------------------------------------------------------
+int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out) {
+    if (!ctx || !out) return PHD_E_BAD_PARAMS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_params(ctx, p, 0);
+    if (rc != PHD_OK) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevParams P;
+    fill_dev_params(P, *p, 1024, 1024, 0, 0, 0);
+    u16* d;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(u16) << 24));
+    phd_launch_group_sweep(P, d, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(u16) << 24, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    CUDA_TRY(ctx, e);
+    return PHD_OK;
+}
+
+int phd_debug_bin_map(phd_context* ctx, int width, int height, int nr, int na, uint16_t* map, int* counts) {
+    if (!ctx) return PHD_E_BAD_PARAMS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ShapePlan* s;
+    int rc = get_shape(ctx, width, height, nr, na, &s);
+    if (rc != PHD_OK) return rc;
+    const size_t nspec = (size_t)(width / 2 + 1) * height;
+    if (map) CUDA_TRY(ctx, cudaMemcpy(map, s->binmap, sizeof(u16) * nspec, cudaMemcpyDeviceToHost));
+    if (counts) CUDA_TRY(ctx, cudaMemcpy(counts, s->bincount, sizeof(int) * nr * na, cudaMemcpyDeviceToHost));
+    return PHD_OK;
+}
+
+int phd_debug_power_spectrum(phd_context* ctx, const uint8_t* rgb, int width, int height, float* power) {
+    if (!ctx || !rgb || !power) return PHD_E_BAD_PARAMS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    phd_params p;
+    phd_default_params(&p);
+    DevParams P;
+    const size_t tight = (size_t)width * height * 3, stride = align_up(tight, 16);
+    fill_dev_params(P, p, width, height, 0, stride, 1);
+    ShapePlan* s;
+    int rc = get_shape(ctx, width, height, P.nr, P.na, &s);
+    if (rc != PHD_OK) return rc;
+    if ((rc = ensure_workspace(ctx, P, 1)) != PHD_OK) return rc;
+    if ((rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, stride)) != PHD_OK) return rc;
+    const size_t nspec = (size_t)P.fw * height;
+    float* d_pow;
+    CUDA_TRY(ctx, cudaMalloc(&d_pow, sizeof(float) * nspec));
+    int launches = 0;
+    cudaError_t e = cudaMemcpyAsync(ctx->d_rgb, rgb, tight, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        if (phd_launch_fft_rows(ctx->d_rgb, P, 1, s->row, ctx->ws.spec, ctx->stream, &launches) ||
+            phd_launch_fft_cols_blur(P, 1, s->col, ctx->ws.spec, s->binmap, ctx->ws, d_pow, ctx->stream, &launches)) {
+            cudaFree(d_pow);
+            return fail(ctx, PHD_E_UNSUPPORTED, "FFT does not fit shared memory");
+        }
+        e = cudaMemcpyAsync(power, d_pow, sizeof(float) * nspec, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_pow);
+    CUDA_TRY(ctx, e);
+    return PHD_OK;
+}
+
+int phd_debug_group_counts(phd_context* ctx, const uint8_t* rgb, int width, int height, const phd_params* p, int* counts) {
+    if (!ctx || !rgb || !counts) return PHD_E_BAD_PARAMS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_params(ctx, p, 0);
+    if (rc != PHD_OK) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevParams P;
+    const size_t tight = (size_t)width * height * 3, stride = align_up(tight, 16);
+    fill_dev_params(P, *p, width, height, 0, stride, 1);
+    ParamTables* tab;
+    if ((rc = get_tables(ctx, *p, &tab)) != PHD_OK) return rc;
+    if ((rc = ensure_workspace(ctx, P, 1)) != PHD_OK) return rc;
+    if ((rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, stride)) != PHD_OK) return rc;
+    int launches = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_rgb, rgb, tight, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, ctx->stream));
+    phd_launch_frontend(ctx->d_rgb, P, 1, tab->centres, ctx->ws, ctx->stream, &launches);
+    CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->ws.hist, sizeof(int) * P.T, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PHD_OK;
+}
+
+// =============================================================================================
+// Part 1: drop-in entry points
+// =============================================================================================
+Full_Report_Data* get_full_report_data(Image_RGB* image, Crop_Boundaries* crop, int h_partitions, int s_partitions,
+                                       int v_partitions, double black_thresh, double gray_thresh,
+                                       double coverage_thresh, int linked_list_size, int downsample_rate,
+                                       int radius_partitions, int angle_partitions, float quantity_weight,
+                                       float saturation_value_weight, double fft_streak_thresh,
+                                       double magnitude_thresh, int blur_cutoff_ratio_denom) {
+    // pre_compute_error_checks, src/utilities.c:64-87, same order and messages
+    if (image == NULL) {
+        fprintf(stderr, "Error: Image pointer is NULL.\n");
+        return NULL;
+    }
+    char why[256];
+    if (reference_rejects(image->width, image->height, why, sizeof(why))) {
+        fprintf(stderr, "%s\n", why);
+        return NULL;
+    }
+    if (image->r == NULL || image->g == NULL || image->b == NULL) {
+        fprintf(stderr, "Error: At least one color channel was a NULL pointer.\n");
+        return NULL;
+    }
+    phd_params p;
+    p.h_partitions = h_partitions; p.s_partitions = s_partitions; p.v_partitions = v_partitions;
+    p.black_thresh = black_thresh; p.gray_thresh = gray_thresh; p.coverage_thresh = coverage_thresh;
+    p.linked_list_size = linked_list_size; p.downsample_rate = downsample_rate;
+    p.radius_partitions = radius_partitions; p.angle_partitions = angle_partitions;
+    p.quantity_weight = quantity_weight; p.saturation_value_weight = saturation_value_weight;
+    p.fft_streak_thresh = fft_streak_thresh; p.magnitude_thresh = magnitude_thresh;
+    p.blur_cutoff_ratio_denom = blur_cutoff_ratio_denom;
+
+    phd_context* ctx = default_context();
+    if (!ctx) return NULL;
+    const int W = image->width, H = image->height;
+    const long long npx = (long long)W * H;
+    const int nb = crop ? crop->N : 0;
+    if (check_params(ctx, &p, nb) != PHD_OK) return NULL;
+    std::vector<int> boxes((size_t)(nb > 0 ? nb : 1) * 4);
+    for (int i = 0; i < nb; i++) {
+        boxes[4 * i] = crop->top[i]; boxes[4 * i + 1] = crop->bottom[i];
+        boxes[4 * i + 2] = crop->left[i]; boxes[4 * i + 3] = crop->right[i];
+        // crop_pgm (src/image_processing.c:215-219) refuses these and the reference then dereferences NULL
+        if (crop->right[i] > W || crop->left[i] > W || crop->bottom[i] > H || crop->top[i] > H || crop->left[i] < 0 ||
+            crop->right[i] < 0 || crop->top[i] < 0 || crop->bottom[i] < 0) {
+            fprintf(stderr, "Error: crop boundaries outside of image boundaries.\n");
+            return NULL;
+        }
+    }
+
+    // planes -> packed 8-bit on the device
+    uint8_t* d_u8 = nullptr;
+    double* d_planes = nullptr;
+    int* d_flag = nullptr;
+    int flag = 0;
+    Full_Report_Data* result = NULL;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        cudaSetDevice(ctx->device);
+        const size_t stride = align_up((size_t)npx * 3, 16);
+        cudaError_t e = cudaMalloc(&d_u8, stride);
+        if (e == cudaSuccess) e = cudaMalloc(&d_planes, sizeof(double) * 3 * (size_t)npx);
+        if (e == cudaSuccess) e = cudaMalloc(&d_flag, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes, image->r, sizeof(double) * npx, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes + npx, image->g, sizeof(double) * npx, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_planes + 2 * npx, image->b, sizeof(double) * npx, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            k_ingest_f64<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(d_planes, d_planes + npx, d_planes + 2 * npx, npx, d_u8, d_flag);
+            e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_planes);
+        cudaFree(d_flag);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "photohive_dsp: CUDA error while uploading the image: %s\n", cudaGetErrorString(e));
+            cudaFree(d_u8);
+            return NULL;
+        }
+    }
+    if (flag) {
+        fprintf(stderr, "photohive_dsp: image values are not of the form k/255 (8-bit); this build only serves 8-bit images\n");
+        cudaFree(d_u8);
+        return NULL;
+    }
+    phd_flat_layout lay;
+    phd_flat_get_layout(&p, nb, &lay);
+    std::vector<unsigned char> rec(lay.record_bytes);
+    const int rc = phd_get_reports_u8(ctx, d_u8, 1, W, H, align_up((size_t)npx * 3, 16), nb > 0 ? boxes.data() : NULL, nb,
+                                      &p, rec.data());
+    cudaFree(d_u8);
+    if (rc != PHD_OK) return NULL;
+    result = phd_flat_to_full_report(rec.data(), &lay);
+    if (result && !crop && result->sharpness) {  // unreachable (n_sharpness = -1 when nb == 0), kept for clarity
+        free(result->sharpness->sharpness);
+        free(result->sharpness);
+        result->sharpness = NULL;
+    }
+    // A non-NULL Crop_Boundaries with N == 0 still yields a Sharpnesses object in the reference (filtering.c:158-160).
+    if (result && crop && !result->sharpness) {
+        result->sharpness = (Sharpnesses*)malloc(sizeof(Sharpnesses));
+        result->sharpness->N = 0;
+        result->sharpness->sharpness = (Pixel*)calloc(1, sizeof(Pixel));
+    }
+    return result;
+}
+
+void free_full_report(Full_Report_Data** report) {
+    if (!report || !*report) return;
+    Full_Report_Data* r = *report;
+    if (r->color_palette) {
+        free(r->color_palette->averages);
+        free(r->color_palette->percentages);
+        free(r->color_palette);
+        r->color_palette = NULL;
+    }
+    if (r->blur_profile) {
+        for (int a = 0; a < r->blur_profile->num_angle_bins; a++) free(r->blur_profile->bins[a]);
+        free(r->blur_profile->bins);
+        free(r->blur_profile);
+        r->blur_profile = NULL;
+    }
+    if (r->blur_vectors) {
+        free(r->blur_vectors->blur_vectors);
+        free(r->blur_vectors);
+        r->blur_vectors = NULL;
+    }
+    if (r->sharpness) {
+        free(r->sharpness->sharpness);
+        free(r->sharpness);
+        r->sharpness = NULL;
+    }
+    free(r->rgb_stats);
+    r->rgb_stats = NULL;
+    free(r);
+    *report = NULL;
+}
+
+// Host-side visualiser, src/blur_profile.c:140-180.  Not on the hot path.
+Image_PGM* get_blur_profile_visual(Blur_Profile* bp, int height, int width) {
+    if (!bp || height <= 0 || width <= 0) return NULL;
+    Image_PGM* out = (Image_PGM*)malloc(sizeof(Image_PGM));
+    if (!out) {
+        fprintf(stderr, "Error creating output image.\n");
+        return NULL;
+    }
+    out->height = height;
+    out->width = width;
+    out->data = (Pixel*)calloc((size_t)height * width, sizeof(Pixel));
+    const double REF_PI = 3.14159265;
+    for (int y = 0; y < height; y++) {
+        const double dy = (y < height / 2) ? -(double)y : (double)(height - y);
+        for (int x = 0; x < width; x++) {
+            const double dx = x;
+            const double r = sqrt(dx * dx + dy * dy);
+            const double phi = atan2(dy, dx);
+            int r_bin = (int)(r / bp->radius_bin_size);
+            if (r_bin >= bp->num_radius_bins) r_bin = bp->num_radius_bins - 1;
+            int phi_bin = (int)((phi + REF_PI * 0.5f) / REF_PI * (double)(bp->num_angle_bins - 1));
+            if (phi_bin >= bp->num_angle_bins) phi_bin = bp->num_angle_bins - 1;
+            if (phi_bin < 0) phi_bin = 0;
+            out->data[(size_t)y * width + x] = bp->bins[phi_bin][r_bin];
+        }
+    }
+    return out;
+}
+
+}  // extern "C"

@@ -318,6 +318,9 @@ void dfft_r2c_2d(int n0, int n1, const double* in, double* out, int nthreads) {
     dfft_plan* prow = dfft_plan_create(n1);
     dfft_plan* pcol = dfft_plan_create(n0);
     if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+    if (nthreads > omp_get_max_threads()) nthreads = omp_get_max_threads(); /* honour OMP_NUM_THREADS */
+#endif
     const int npairs = (n0 + 1) / 2;
 #ifdef _OPENMP
 #pragma omp parallel num_threads(nthreads)

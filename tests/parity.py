@@ -1,0 +1,80 @@
+"""Comparison rules shared by the parity tests.
+
+Tolerances (BASELINE.json north_star: bit-exact integers, <= 1e-4 relative for floating point).  What the
+implementation actually achieves is far tighter, and the tests pin that so regressions show:
+
+  integer outputs (palette N, parent order, angle/radius bin sizes, blur-vector angles, group counts,
+  bin-id map, tie/dropped pixel counts)                        : exact
+  palette percentages (count / P)                              : 1e-15 absolute (same integers, same division)
+  rgb_stats, average_saturation, sharpness, palette s and v    : 1e-9 relative
+  palette hue (degrees, circular quantity)                     : 1e-6 absolute
+  blur-profile bins (FP32 transform vs the reference's FP64)   : 1e-4 relative with a 2e-6 absolute floor
+  blur-vector magnitudes (k / nr as float)                     : exact
+"""
+import numpy as np
+
+RTOL_STATS = 1e-9
+ATOL_HUE = 1e-6
+RTOL_BINS = 1e-4
+ATOL_BINS = 2e-6
+
+
+def rel_err(a, b, floor=1e-300):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def assert_report_close(got, want, what=""):
+    """got / want: oracle.binding.Report-like objects (numpy fields)."""
+    assert np.all(rel_err(got.rgb_stats, want.rgb_stats, 1e-12) < RTOL_STATS), f"{what}: rgb_stats"
+    assert rel_err(got.average_saturation, want.average_saturation, 1e-12) < RTOL_STATS, f"{what}: average_saturation"
+    assert len(got.palette_pct) == len(want.palette_pct), f"{what}: palette N {len(got.palette_pct)} != {len(want.palette_pct)}"
+    assert np.max(np.abs(got.palette_pct - want.palette_pct), initial=0) <= 1e-15, f"{what}: palette percentages"
+    if len(want.palette_pct):
+        dh = np.abs(got.palette_hsv[:, 0] - want.palette_hsv[:, 0])
+        dh = np.minimum(dh, 360 - dh)
+        assert np.max(dh) < ATOL_HUE, f"{what}: palette hue {np.max(dh)}"
+        assert np.all(rel_err(got.palette_hsv[:, 1:], want.palette_hsv[:, 1:], 1e-12) < RTOL_STATS), f"{what}: palette s/v"
+    assert got.angle_bin_size == want.angle_bin_size and got.radius_bin_size == want.radius_bin_size, f"{what}: bin sizes"
+    d = np.abs(got.blur_bins - want.blur_bins)
+    assert np.all(d <= ATOL_BINS + RTOL_BINS * np.abs(want.blur_bins)), f"{what}: blur bins max abs {d.max()}"
+    assert np.array_equal((got.blur_bins == 0), (want.blur_bins == 0)), f"{what}: empty-bin pattern"
+    assert np.array_equal(got.blur_vec_angle, want.blur_vec_angle), f"{what}: blur vector angles"
+    assert np.array_equal(got.blur_vec_mag, want.blur_vec_mag), f"{what}: blur vector magnitudes"
+    if want.sharpness is None:
+        assert got.sharpness is None or len(got.sharpness) == 0, f"{what}: unexpected sharpness"
+    else:
+        assert got.sharpness is not None and len(got.sharpness) == len(want.sharpness), f"{what}: sharpness count"
+        assert np.all(rel_err(got.sharpness, want.sharpness, 1e-12) < RTOL_STATS), f"{what}: sharpness"
+
+
+def report_from_batch(b, i):
+    """One record of a photohive_dsp_b200.batch.BatchReports as an oracle.binding.Report."""
+    from oracle.binding import Report
+    n = int(b.palette_n[i])
+    return Report(rgb_stats=b.rgb_stats[i].copy(), average_saturation=float(b.average_saturation[i]),
+                  palette_hsv=b.palette_hsv[i, :n].copy(), palette_pct=b.palette_pct[i, :n].copy(),
+                  blur_bins=b.blur_bins[i].copy(), angle_bin_size=int(b.angle_bin_size[i]),
+                  radius_bin_size=int(b.radius_bin_size[i]), blur_vec_angle=b.blur_vec_angle[i].copy(),
+                  blur_vec_mag=b.blur_vec_mag[i].copy(),
+                  sharpness=None if b.sharpness is None else b.sharpness[i].copy(),
+                  extra=dict(parent_ids=b.parent_ids[i, :n].copy(), tie_groups=int(b.tie_groups[i]),
+                             dropped_pixels=int(b.dropped_pixels[i])))
+
+
+def golden_report(golden, name):
+    from oracle.binding import Report
+    ints = golden.field(name, "ints")
+    return Report(rgb_stats=golden.field(name, "rgb_stats"), average_saturation=float(golden.field(name, "average_saturation")),
+                  palette_hsv=golden.field(name, "palette_hsv"), palette_pct=golden.field(name, "palette_pct"),
+                  blur_bins=golden.field(name, "blur_bins"), angle_bin_size=int(ints[0]), radius_bin_size=int(ints[1]),
+                  blur_vec_angle=golden.field(name, "blur_vec_angle"), blur_vec_mag=golden.field(name, "blur_vec_mag"),
+                  sharpness=golden.field(name, "sharpness"))
+
+
+def boxes_array(meta_boxes, n=1):
+    if not meta_boxes:
+        return None
+    one = [[b["top"], b["bottom"], b["left"], b["right"]] for b in meta_boxes]
+    return np.array([one] * n, np.int32)

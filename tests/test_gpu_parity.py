@@ -1,0 +1,204 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle, the committed
+reference golden vectors, and size-independent properties at BASELINE.json's full sizes.  Run with -m gpu."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle.binding import make_params as omake
+from parity import assert_report_close, boxes_array, golden_report, rel_err, report_from_batch
+from photohive_dsp_b200.batch import make_params
+
+pytestmark = pytest.mark.gpu
+
+FINE = dict(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99)
+
+
+# ---- discrete stages: bit exact --------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [{}, FINE, dict(h_partitions=12, s_partitions=3, v_partitions=5, black_thresh=0.15, gray_thresh=0.2),
+                                dict(h_partitions=24, s_partitions=1, v_partitions=1)])
+def test_group_id_of_all_2pow24_colours(ctx, oracle, kw):
+    """the palette group of every 24-bit colour equals the reference arithmetic, bit for bit."""
+    got = ctx.debug_group_sweep(make_params(**kw))
+    want = oracle.group_sweep(omake(**kw))
+    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} colours land in another group"
+
+
+@pytest.mark.parametrize("shape", [(1920, 1080), (3840, 2160), (6000, 4000), (405, 357), (1080, 1920), (350, 350)])
+def test_polar_bin_map_is_identical(ctx, oracle, shape):
+    """bin ids (truncated PI, Newton sqrt, bottom-half row rule) and bin populations."""
+    assert all(_largest_prime(s) <= 31 for s in shape)  # lengths this build's radix set covers
+    m, c = ctx.debug_bin_map(*shape)
+    mo, co = oracle.bin_map(*shape)
+    assert np.array_equal(m, mo) and np.array_equal(c, co)
+
+
+def _largest_prime(n):
+    best, p = 1, 2
+    while p * p <= n:
+        while n % p == 0:
+            best, n = p, n // p
+        p += 1
+    return max(best, n) if n > 1 else best
+
+
+@pytest.mark.parametrize("kind,kw", [(0, {}), (1, {}), (1, dict(downsample_rate=3)), (0, FINE)])
+def test_group_counts_bit_exact(ctx, oracle, kind, kw):
+    img = oracle.generate(kind, 4242 + kind, 1280, 720)
+    got = ctx.debug_group_counts(img, make_params(**kw))
+    want = oracle.report(img, omake(**kw), stages=1).extra["group_counts"]
+    assert np.array_equal(got, want)
+    ds = kw.get("downsample_rate", 1)
+    assert got.sum() == (1280 // ds) * (720 // ds)
+
+
+# ---- full reports ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["g1_small", "g0_small", "g2_small", "g1_odd2", "g0_fine", "g1_down5", "g1_list50", "g2_cov1",
+                                  "g1_1080p", "g0_1080p", "g2_1080p"])
+def test_report_matches_reference_golden(ctx, oracle, golden, name):
+    """Against outputs of the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    m = golden.meta[name]
+    img = golden.image(oracle, name)
+    b = ctx.get_reports(img[None], boxes=boxes_array(m["boxes"]), params=make_params(**m["params"]))
+    assert_report_close(report_from_batch(b, 0), golden_report(golden, name), name)
+
+
+@pytest.mark.parametrize("W,H,kind,kw", [
+    (1920, 1080, 1, {}), (1000, 750, 0, {}), (1280, 960, 2, dict(linked_list_size=16)),
+    (700, 525, 1, dict(h_partitions=9, s_partitions=3, v_partitions=4, coverage_thresh=0.9)),
+    (1024, 768, 0, dict(downsample_rate=2, radius_partitions=16, angle_partitions=36)),
+    (3840, 2160, 1, {}),   # BASELINE config 2: 4K with four salient boxes
+])
+def test_report_matches_oracle(ctx, oracle, W, H, kind, kw):
+    img = oracle.generate(kind, 1000 + W + kind, W, H)
+    boxes = [dict(top=H * i // 8, bottom=H * i // 8 + H // 4, left=W * i // 8, right=W * i // 8 + W // 4) for i in range(4)]
+    want = oracle.report(img, omake(**kw), boxes=boxes, nthreads=8)
+    b = ctx.get_reports(img[None], boxes=boxes_array(boxes), params=make_params(**kw))
+    got = report_from_batch(b, 0)
+    assert_report_close(got, want, f"{W}x{H} kind {kind} {kw}")
+    assert np.array_equal(got.extra["parent_ids"], want.extra["parent_ids"])
+    assert got.extra["tie_groups"] == want.extra["tie_groups"]
+    assert got.extra["dropped_pixels"] == want.extra["dropped_pixels"]
+
+
+def test_batch_is_deterministic_and_position_independent(ctx, oracle):
+    """Integer accumulators: a record does not depend on where the image sits in a batch, nor on the run."""
+    imgs = np.stack([oracle.generate(k % 3, 50 + k, 640, 480) for k in range(7)])
+    a = ctx.get_reports(imgs)
+    b = ctx.get_reports(imgs[::-1].copy())
+    c = ctx.get_reports(imgs)
+    assert np.array_equal(a.raw, c.raw)
+    assert np.array_equal(a.raw, b.raw[::-1])
+
+
+def test_device_resident_input_equals_host_input(ctx, oracle):
+    import torch
+    imgs = np.stack([oracle.generate(k, 9 + k, 800, 600) for k in range(3)])
+    host = ctx.get_reports(imgs)
+    dev = ctx.get_reports(torch.from_numpy(imgs).cuda())
+    assert np.array_equal(host.raw, dev.raw)
+
+
+def test_edge_images(ctx, oracle):
+    """Flat, black, white and two-colour images: empty spectrum, single group, max==1 clamps."""
+    H, W = 400, 560
+    cases = {
+        "black": np.zeros((H, W, 3), np.uint8),
+        "white": np.full((H, W, 3), 255, np.uint8),
+        "gray": np.full((H, W, 3), 128, np.uint8),
+        "red": np.tile(np.array([255, 0, 0], np.uint8), (H, W, 1)),
+    }
+    half = np.zeros((H, W, 3), np.uint8)
+    half[:, W // 2:] = [10, 200, 30]
+    cases["two"] = half
+    for name, img in cases.items():
+        want = oracle.report(img, omake(), nthreads=4)
+        got = report_from_batch(ctx.get_reports(img[None]), 0)
+        # contrast of a constant image is rounding noise in the reference (1e-17) and exactly 0 here
+        got.rgb_stats[3:] = np.where(np.abs(want.rgb_stats[3:]) < 1e-12, want.rgb_stats[3:], got.rgb_stats[3:])
+        assert_report_close(got, want, name)
+
+
+# ---- drop-in entry point ---------------------------------------------------------------------------
+def test_drop_in_entry_point_matches_oracle(oracle, capfd):
+    """get_full_report_data on planar doubles k/255.0, exactly as core.py:442-469 calls it."""
+    from oracle import binding
+    from photohive_dsp_b200 import lib as L
+    img = oracle.generate(1, 31337, 960, 540)
+    boxes = [dict(top=10, bottom=200, left=20, right=400), dict(top=100, bottom=540, left=480, right=960)]
+    lib = binding.bind_entry_points(C.CDLL(L.lib_path))
+    rp = binding.call_entry_point(lib, binding.planes_from_u8(img), 960, 540, omake(), boxes)
+    assert rp
+    got = binding.unpack_full_report(rp)
+    lib.free_full_report(C.byref(rp))
+    assert not rp
+    assert got.extra["len_vectors"] == 10
+    assert_report_close(got, oracle.report(img, omake(), boxes=boxes, nthreads=4), "drop-in")
+    # no boxes -> sharpness pointer is NULL (src/filtering.c:152-154)
+    rp = binding.call_entry_point(lib, binding.planes_from_u8(img), 960, 540, omake(), None)
+    assert rp and not rp.contents.sharpness
+    lib.free_full_report(C.byref(rp))
+
+
+def test_python_get_report_surface(oracle):
+    """get_report / set_bounding_boxes / Report keep the reference's Python surface (core.py:23-119,388-515)."""
+    import json
+    import photohive_dsp_b200 as P
+    img = oracle.generate(2, 5, 640, 480)
+    bb = P.set_bounding_boxes([dict(top=0, bottom=240, left=0, right=320)])
+    rep = P.get_report(img, salient_characters=bb)
+    want = oracle.report(img, omake(), boxes=[dict(top=0, bottom=240, left=0, right=320)], nthreads=4)
+    assert rep is not None and rep.rgb_stats.height == 480 and rep.rgb_stats.width == 640
+    assert abs(rep.rgb_stats.Br - want.rgb_stats[0]) < 1e-12 and abs(rep.average_saturation - want.average_saturation) < 1e-9
+    assert len(rep.blur_vectors) == 10 and len(rep.blur_profile.bins) == 72 and len(rep.blur_profile.bins[0]) == 40
+    assert len(rep.color_palette.colors) == len(want.palette_pct) and len(rep.sharpnesses) == 1
+    js = json.loads(rep.to_json())
+    assert js["Height"] == 480 and abs(js["Sharpness 1:"] - want.sharpness[0]) < 1e-9 * abs(want.sharpness[0])
+    vis = rep.generate_blur_profile_image()
+    assert vis.size == (320, 480)
+    assert P.get_report(np.zeros((349, 350, 3), np.uint8)) is None
+
+
+def test_non_8bit_image_is_refused_loudly(capfd):
+    from oracle import binding
+    from photohive_dsp_b200 import lib as L
+    lib = binding.bind_entry_points(C.CDLL(L.lib_path))
+    planes = tuple(np.full(400 * 400, 0.1234567, np.float64) for _ in range(3))
+    assert not binding.call_entry_point(lib, planes, 400, 400, omake(), None)
+    assert "8-bit" in capfd.readouterr().err
+
+
+# ---- full-size, size-independent properties --------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(3840, 2160), (6000, 4000)])
+def test_full_size_properties(ctx, oracle, W, H):
+    """BASELINE configs 2 and 4 (4K, 24 MP): invariants that need no CPU run of the whole pipeline."""
+    img = oracle.generate(1, 2024, W, H)
+    P = W * H
+    p = make_params()
+    b = ctx.get_reports(img[None], params=p)
+    n = int(b.palette_n[0])
+    # palette: every pixel is counted once or dropped by the tie path; parents are distinct groups
+    assert abs(b.palette_pct[0, :n].sum() - (1 - int(b.dropped_pixels[0]) / P)) < 1e-12
+    assert len(set(b.parent_ids[0, :n].tolist())) == n
+    counts = ctx.debug_group_counts(img, p)
+    assert counts.sum() == P
+    # exact channel statistics from integer sums
+    x = img.reshape(-1, 3).astype(np.float64) / 255.0
+    assert np.all(rel_err(b.rgb_stats[0, :3], x.mean(0)) < 1e-12)
+    assert np.all(rel_err(b.rgb_stats[0, 3:], x.std(0)) < 1e-9)
+    # Parseval on the hand-written 2-D FFT: sum over the full spectrum of |X|^2 == W*H * sum x^2
+    pw = ctx.debug_power_spectrum(img).astype(np.float64)
+    gnum = (299 * img[:, :, 0].astype(np.int64) + 587 * img[:, :, 1] + 114 * img[:, :, 2]) - 127500
+    energy = float(np.sum(gnum.astype(np.float64) ** 2)) / 255000.0 ** 2 * P
+    wts = np.full(W // 2 + 1, 2.0)
+    wts[0] = 1.0
+    if W % 2 == 0:
+        wts[-1] = 1.0
+    assert abs(np.sum(pw * wts[None, :]) - energy) / energy < 1e-5
+    # DC bin is the plain sum
+    assert abs(np.sqrt(pw[0, 0]) - abs(gnum.sum()) / 255000.0) / (abs(gnum.sum()) / 255000.0) < 1e-5
+    # bins: empty-bin pattern comes from the (exact) bin map; values are normalised to [0, 1]
+    _, cnt = ctx.debug_bin_map(W, H)
+    assert np.array_equal(b.blur_bins[0] == 0, cnt == 0) or np.all(b.blur_bins[0][cnt == 0] == 0)
+    assert b.blur_bins[0].max() <= 1.0 + 1e-9 and b.blur_bins[0].min() >= 0

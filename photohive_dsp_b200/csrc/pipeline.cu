@@ -348,6 +348,8 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
                                           cudaMemcpyHostToDevice, st));
         }
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
+        // records carry padding bytes no kernel writes: clear them so equal images give equal bytes
+        CUDA_TRY(ctx, cudaMemsetAsync(records_dev + (size_t)first * lay.record_bytes, 0, lay.record_bytes * (size_t)n, st));
         cudaEvent_t* ev = &ctx->events[2 + (size_t)sb * 8];
         CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
         phd_launch_frontend(d_in, P, n, tab->centres, ctx->ws, st, &launches);

@@ -216,7 +216,8 @@ PHD_API Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_
 PHD_API int phd_last_timing(const phd_context* ctx, float ms[8]);
 
 /* Test hooks (parity tests call these through the C ABI; they are not needed by applications). */
-PHD_API int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out_2pow24 /* host */);
+PHD_API int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out_2pow24 /* host */);       /* product path (integer fast path + FP64 edge path) */
+PHD_API int phd_debug_group_sweep_exact(phd_context* ctx, const phd_params* p, uint16_t* out_2pow24 /* host */); /* FP64 transcription of the reference arithmetic */
 PHD_API int phd_debug_bin_map(phd_context* ctx, int width, int height, int nr, int na,
                       uint16_t* map /* host, height*(width/2+1) */, int* counts /* host, na*nr */);
 PHD_API int phd_debug_power_spectrum(phd_context* ctx, const uint8_t* rgb /* host */, int width, int height,

@@ -157,9 +157,11 @@ class Context:
         return dict(zip(names, [float(x) for x in ms])), launches
 
     # ---- test hooks ---------------------------------------------------------------------------------
-    def debug_group_sweep(self, params: phd_params) -> np.ndarray:
+    def debug_group_sweep(self, params: phd_params, exact: bool = False) -> np.ndarray:
+        """Group id of all 2^24 colours: product path, or (exact=True) the FP64 transcription."""
         out = np.empty(1 << 24, np.uint16)
-        self._check(lib.phd_debug_group_sweep(self._h, C.byref(params), out.ctypes.data_as(C.c_void_p)))
+        fn = lib.phd_debug_group_sweep_exact if exact else lib.phd_debug_group_sweep
+        self._check(fn(self._h, C.byref(params), out.ctypes.data_as(C.c_void_p)))
         return out
 
     def debug_bin_map(self, width, height, nr=40, na=72):

@@ -1,86 +1,191 @@
 // Hand-written 2-D real FFT of the grayscale image with the blur-profile binning fused into the
 // column pass.  No cuFFT anywhere in the library.
 //
-//   k_fft_rows       first half of pgm_fft (src/fft_processing.c:18-63) with rgb2pgm fused in front
-//                    (src/image_processing.c:505-512): two image rows are read as packed RGB, turned
-//                    into the exact integer gray numerators 299R+587G+114B, packed as one complex
-//                    sequence, transformed in shared memory (Stockham autosort, mixed radix) and
-//                    split into the two half spectra.  A constant 127500 (= 0.5 gray) is removed
-//                    before the transform for FP32 headroom; DC is repaired exactly in the epilogue.
-//   k_fft_cols_blur  second half of pgm_fft, remove_dc_bias (src/blur_profile.c:233-238),
-//                    pgm_normalize_fft (src/fft_processing.c:173-200) and the accumulation loop of
-//                    calculate_blur_profile (src/blur_profile.c:87-100): column tiles are transformed
-//                    in shared memory, then power -> (p<1 ? 0 : ln p) -> polar bin (cached id map) ->
-//                    shared-memory integer bins -> 64-bit global integer bins; max power by atomicMax.
-//                    G_s is a scalar and is applied after averaging, in finalize.
-//   k_bin_map        cartesian_to_polar_conversion + the bin index arithmetic
-//                    (src/blur_profile.c:427-458, :94-97; newton_int_sqrt src/utilities.c:43-52),
-//                    image independent, built once per (W,H,nr,na) and cached.
+// Data flow (per image):  packed RGB --k_rows--> specT[x][k] (row-transformed half spectrum, TRANSPOSED so a
+// spectrum column is contiguous) --k_cols--> integer blur bins + max power.  The final spectrum is never
+// written: power, ln, polar binning happen in the column kernel's epilogue.
+//
+//   k_rows_t / k_rows_generic   first half of pgm_fft (src/fft_processing.c:18-63) with rgb2pgm fused in front
+//       (src/image_processing.c:505-512).  Rows are read as packed RGB, turned into the exact integer gray
+//       numerators 299R+587G+114B, two rows are packed as one complex sequence, transformed in shared memory
+//       (Stockham autosort) and split into the two half spectra.  A constant 127500 (= 0.5 gray) is removed
+//       before the transform for FP32 headroom; DC is repaired exactly in the column epilogue.
+//   k_cols_t / k_cols_generic   second half of pgm_fft, remove_dc_bias (src/blur_profile.c:233-238),
+//       pgm_normalize_fft (src/fft_processing.c:173-200) and the accumulation loop of calculate_blur_profile
+//       (src/blur_profile.c:87-100).  Columns (contiguous in specT) and the matching slice of the bin-id map
+//       are staged into shared memory with cp.async.bulk (the TMA copy engine) signalled through an mbarrier,
+//       transformed, then power -> (p<1 ? 0 : ln p) -> polar bin -> run-length merged per thread ->
+//       shared-memory integer bins -> 64-bit global integer bins; max power by atomicMax.
+//       G_s is a scalar and is applied after averaging, in finalize.
+//   k_bin_map   cartesian_to_polar_conversion + the bin index arithmetic (src/blur_profile.c:427-458, :94-97;
+//       newton_int_sqrt src/utilities.c:43-52); image independent, built once per (W,H,nr,na) and cached.
+//
+// The *_t kernels are compile-time specialised (length and radix plan as template arguments: radix-15/16/25...
+// register butterflies with folded constants) for the shapes of BASELINE.json; every other size whose prime
+// factors are <= 31 runs the *_generic kernels (runtime radix list 4/2/3/5/p).
 #include <math.h>
 
+#include "fft_tables.cuh"
 #include "phd_internal.h"
 
 namespace {
+
+#define PHD_GRAY_BIAS 127500
+constexpr int kRowThreads = 256;
+constexpr int kColThreads = 512;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 __device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// multiply by -i
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // * -i
 
+// ------------------------------------------------------------------------------------------
+// Register butterflies.  Radix<R>::run is an in-place R-point DFT, natural order in and out.
+// ------------------------------------------------------------------------------------------
+template <int R> struct Radix;
+
+template <> struct Radix<2> {
+    static __device__ __forceinline__ void run(float2 (&x)[2]) {
+        const float2 a = x[0], b = x[1];
+        x[0] = caddf(a, b);
+        x[1] = csubf(a, b);
+    }
+};
+template <> struct Radix<4> {
+    static __device__ __forceinline__ void run(float2 (&x)[4]) {
+        const float2 t0 = caddf(x[0], x[2]), t1 = csubf(x[0], x[2]);
+        const float2 t2 = caddf(x[1], x[3]), t3 = mul_mi(csubf(x[1], x[3]));
+        x[0] = caddf(t0, t2);
+        x[1] = caddf(t1, t3);
+        x[2] = csubf(t0, t2);
+        x[3] = csubf(t1, t3);
+    }
+};
+template <> struct Radix<3> {
+    static __device__ __forceinline__ void run(float2 (&x)[3]) {
+        const float k3 = 0.86602540378443864676f;
+        const float2 t = caddf(x[1], x[2]);
+        const float2 u = make_float2(x[0].x - 0.5f * t.x, x[0].y - 0.5f * t.y);
+        const float2 d = csubf(x[1], x[2]);
+        const float2 v = make_float2(k3 * d.y, -k3 * d.x);
+        x[0] = caddf(x[0], t);
+        x[1] = caddf(u, v);
+        x[2] = csubf(u, v);
+    }
+};
+template <> struct Radix<5> {
+    static __device__ __forceinline__ void run(float2 (&x)[5]) {
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        const float2 t1 = caddf(x[1], x[4]), t2 = caddf(x[2], x[3]);
+        const float2 t3 = csubf(x[1], x[4]), t4 = csubf(x[2], x[3]);
+        const float2 m1 = make_float2(x[0].x + c1 * t1.x + c2 * t2.x, x[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 m2 = make_float2(x[0].x + c2 * t1.x + c1 * t2.x, x[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        const float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        x[0] = make_float2(x[0].x + t1.x + t2.x, x[0].y + t1.y + t2.y);
+        x[1] = make_float2(m1.x + n1.y, m1.y - n1.x);
+        x[4] = make_float2(m1.x - n1.y, m1.y + n1.x);
+        x[2] = make_float2(m2.x + n2.y, m2.y - n2.x);
+        x[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
+    }
+};
+
+// RA*RB-point DFT from RA- and RB-point ones (Cooley-Tukey in registers, constants folded at compile time):
+// n = n1*RB + n2, k = k1 + RA*k2;  X[k] = sum_n2 W_N^(n2 k1) [sum_n1 x[n] W_RA^(n1 k1)] W_RB^(n2 k2).
+template <int RA, int RB>
+struct Composite {
+    static __device__ __forceinline__ void run(float2 (&x)[RA * RB]) {
+        constexpr int N = RA * RB;
+        float2 t[N];
+#pragma unroll
+        for (int n2 = 0; n2 < RB; n2++) {
+            float2 y[RA];
+#pragma unroll
+            for (int n1 = 0; n1 < RA; n1++) y[n1] = x[n1 * RB + n2];
+            Radix<RA>::run(y);
+#pragma unroll
+            for (int k1 = 0; k1 < RA; k1++) {
+                const int e = (n2 * k1) % N;
+                if (e == 0) t[n2 * RA + k1] = y[k1];
+                else {
+                    const float c = PhdTw<N>::c(e), s = PhdTw<N>::s(e);
+                    t[n2 * RA + k1] = make_float2(y[k1].x * c - y[k1].y * s, y[k1].x * s + y[k1].y * c);
+                }
+            }
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < RA; k1++) {
+            float2 z[RB];
+#pragma unroll
+            for (int n2 = 0; n2 < RB; n2++) z[n2] = t[n2 * RA + k1];
+            Radix<RB>::run(z);
+#pragma unroll
+            for (int k2 = 0; k2 < RB; k2++) x[k1 + RA * k2] = z[k2];
+        }
+    }
+};
+template <> struct Radix<6> : Composite<2, 3> {};
+template <> struct Radix<8> : Composite<2, 4> {};
+template <> struct Radix<9> : Composite<3, 3> {};
+template <> struct Radix<10> : Composite<2, 5> {};
+template <> struct Radix<12> : Composite<3, 4> {};
+template <> struct Radix<15> : Composite<3, 5> {};
+template <> struct Radix<16> : Composite<4, 4> {};
+template <> struct Radix<25> : Composite<5, 5> {};
+
+// One Stockham pass, compile-time length N, radix R, stride S (product of the radices already applied), over
+// nfft sequences laid out fstride apart in shared memory.  Reads are unit stride across lanes; the first pass
+// (S == 1) writes with stride R, which is why the plans start with an odd radix (conflict-free 8-byte stores).
+template <int N, int R, int S>
+__device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
+                                       const float2* __restrict__ tw, int nfft, int fstride) {
+    constexpr int M = N / R;
+    const int total = nfft * M;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int f = idx / M;
+        const int b = idx - f * M;
+        const int q = b % S;
+        const int pps = b - q;
+        const float2* a = in + f * fstride;
+        float2* y = out + f * fstride;
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = a[b + k * M];
+        Radix<R>::run(x);
+        if (S * R == N) {  // last pass: every twiddle is 1
+#pragma unroll
+            for (int j = 0; j < R; j++) y[q + j * S] = x[j];
+        } else {
+            y[R * pps + q] = x[0];
+#pragma unroll
+            for (int j = 1; j < R; j++) y[R * pps + q + j * S] = cmulf(x[j], __ldg(&tw[pps * j]));
+        }
+    }
+}
+
+// Up to four passes; R3 == 1 means a three-pass plan.  Returns the buffer holding the result.
+template <int N, int R0, int R1, int R2, int R3>
+__device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ tw, int nfft, int fstride) {
+    static_assert(R0 * R1 * R2 * R3 == N, "radix plan does not multiply to N");
+    pass_t<N, R0, 1>(a, b, tw, nfft, fstride);
+    __syncthreads();
+    pass_t<N, R1, R0>(b, a, tw, nfft, fstride);
+    __syncthreads();
+    pass_t<N, R2, R0 * R1>(a, b, tw, nfft, fstride);
+    __syncthreads();
+    if (R3 == 1) return b;
+    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2)>(b, a, tw, nfft, fstride);
+    __syncthreads();
+    return a;
+}
+
+// ---- runtime-radix fallback (any length whose prime factors are <= 31) -----------------------
 template <int R>
-__device__ __forceinline__ void butterfly(float2 (&x)[R]);
-
-template <>
-__device__ __forceinline__ void butterfly<2>(float2 (&x)[2]) {
-    float2 a = x[0], b = x[1];
-    x[0] = caddf(a, b);
-    x[1] = csubf(a, b);
-}
-template <>
-__device__ __forceinline__ void butterfly<4>(float2 (&x)[4]) {
-    float2 t0 = caddf(x[0], x[2]), t1 = csubf(x[0], x[2]);
-    float2 t2 = caddf(x[1], x[3]), t3 = mul_mi(csubf(x[1], x[3]));
-    x[0] = caddf(t0, t2);
-    x[1] = caddf(t1, t3);
-    x[2] = csubf(t0, t2);
-    x[3] = csubf(t1, t3);
-}
-template <>
-__device__ __forceinline__ void butterfly<3>(float2 (&x)[3]) {
-    const float k3 = 0.86602540378443864676f;
-    float2 t = caddf(x[1], x[2]);
-    float2 u = make_float2(x[0].x - 0.5f * t.x, x[0].y - 0.5f * t.y);
-    float2 d = csubf(x[1], x[2]);
-    float2 v = make_float2(k3 * d.y, -k3 * d.x);
-    x[0] = caddf(x[0], t);
-    x[1] = caddf(u, v);
-    x[2] = csubf(u, v);
-}
-template <>
-__device__ __forceinline__ void butterfly<5>(float2 (&x)[5]) {
-    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    float2 t1 = caddf(x[1], x[4]), t2 = caddf(x[2], x[3]);
-    float2 t3 = csubf(x[1], x[4]), t4 = csubf(x[2], x[3]);
-    float2 m1 = make_float2(x[0].x + c1 * t1.x + c2 * t2.x, x[0].y + c1 * t1.y + c2 * t2.y);
-    float2 m2 = make_float2(x[0].x + c2 * t1.x + c1 * t2.x, x[0].y + c2 * t1.y + c1 * t2.y);
-    float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-    float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-    x[0] = make_float2(x[0].x + t1.x + t2.x, x[0].y + t1.y + t2.y);
-    x[1] = make_float2(m1.x + n1.y, m1.y - n1.x);
-    x[4] = make_float2(m1.x - n1.y, m1.y + n1.x);
-    x[2] = make_float2(m2.x + n2.y, m2.y - n2.x);
-    x[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
-}
-
-// One Stockham pass of radix R over `nbatch` sequences of length n laid out `bstride` apart.
-// in/out are shared-memory buffers; s is the product of the radices already applied.
-template <int R>
-__device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
-                                         const float2* __restrict__ tw, int nbatch, int bstride) {
+__device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
+                                        const float2* __restrict__ tw, int nbatch, int bstride) {
     const int m = n / R;
     const int total = nbatch * m;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -93,16 +198,15 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
         float2 x[R];
 #pragma unroll
         for (int k = 0; k < R; k++) x[k] = a[b + k * m];
-        butterfly<R>(x);
+        Radix<R>::run(x);
         y[R * pps + q] = x[0];
 #pragma unroll
         for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf(x[j], __ldg(&tw[pps * j]));
     }
 }
 
-// Generic odd prime radix (7..31): O(r^2) butterfly with table twiddles.
-__device__ void fft_pass_generic(int r, const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
-                                 const float2* __restrict__ tw, int nbatch, int bstride) {
+__device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
+                              const float2* __restrict__ tw, int nbatch, int bstride) {
     const int m = n / r;
     const int total = nbatch * m;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -120,19 +224,18 @@ __device__ void fft_pass_generic(int r, const float2* __restrict__ in, float2* _
     }
 }
 
-// Runs every pass; returns the buffer that holds the result.
-__device__ float2* fft_run(const FftPlan& pl, float2* bufA, float2* bufB, int nbatch, int bstride) {
+__device__ float2* fft_run_rt(const FftPlan& pl, float2* bufA, float2* bufB, int nbatch, int bstride) {
     float2* a = bufA;
     float2* b = bufB;
     int s = 1;
     for (int f = 0; f < pl.nfac; f++) {
         const int r = pl.fac[f];
         switch (r) {
-            case 2: fft_pass<2>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            case 3: fft_pass<3>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            case 4: fft_pass<4>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            case 5: fft_pass<5>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            default: fft_pass_generic(r, a, b, pl.n, s, pl.tw, nbatch, bstride); break;
+            case 2: pass_rt<2>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
+            case 3: pass_rt<3>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
+            case 4: pass_rt<4>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
+            case 5: pass_rt<5>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
+            default: pass_rt_prime(r, a, b, pl.n, s, pl.tw, nbatch, bstride); break;
         }
         __syncthreads();
         s *= r;
@@ -149,10 +252,63 @@ __global__ void k_twiddles(float2* tw, int n) {
     tw[k] = make_float2((float)c, (float)(-s));
 }
 
+__device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
+    return 299 * (int)__ldg(p) + 587 * (int)__ldg(p + 1) + 114 * (int)__ldg(p + 2);
+}
+
 // ------------------------------------------------------------------------------------------
-// Row pass: one CTA per row pair.
-__global__ void __launch_bounds__(256) k_fft_rows(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
-                                                  float2* __restrict__ spec) {
+// Rows, specialised: one CTA transforms four image rows (two packed complex sequences) and writes, for every
+// spectrum column x, the four consecutive entries specT[x][4j..4j+3] as one 32-byte sector.
+// Requires W % 16 == 0, H % 4 == 0, 16-byte aligned rows.
+// ------------------------------------------------------------------------------------------
+template <int N, int R0, int R1, int R2, int R3>
+__global__ void __launch_bounds__(kRowThreads) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
+                                                        const float2* __restrict__ tw, float2* __restrict__ specT) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);
+    float2* bufB = bufA + 2 * N;
+    const int img = blockIdx.y, r0 = 4 * blockIdx.x;
+    const uint8_t* base = rgb + (size_t)img * P.image_stride + (size_t)r0 * N * 3;
+    // 4 rows x N/16 segments of 16 pixels (48 bytes = three 16-byte loads)
+    constexpr int SEGS = N / 16;
+    for (int task = threadIdx.x; task < 4 * SEGS; task += blockDim.x) {
+        const int row = task / SEGS, seg = task - row * SEGS;
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)row * N * 3 + (size_t)seg * 48);
+        const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        const u32 w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        float* dst = reinterpret_cast<float*>(bufA + (row >> 1) * N + seg * 16) + (row & 1);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int R = (w[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 255;
+            const int G = (w[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3))) & 255;
+            const int B = (w[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3))) & 255;
+            dst[2 * i] = (float)(299 * R + 587 * G + 114 * B - PHD_GRAY_BIAS);
+        }
+    }
+    __syncthreads();
+    const float2* z = fft_run_t<N, R0, R1, R2, R3>(bufA, bufB, tw, 2, N);
+    const int fw = N / 2 + 1;
+    float2* out = specT + (size_t)img * fw * P.Hp + r0;
+    for (int k = threadIdx.x; k < fw; k += blockDim.x) {
+        const int kc = k == 0 ? 0 : N - k;
+        float4 lo, hi;
+        {
+            const float2 zk = z[k], zc = z[kc];
+            lo = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+        }
+        {
+            const float2 zk = z[N + k], zc = z[N + kc];
+            hi = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+        }
+        float4* o = reinterpret_cast<float4*>(out + (size_t)k * P.Hp);
+        o[0] = lo;
+        o[1] = hi;
+    }
+}
+
+// Rows, generic: one CTA per row pair, runtime radix plan.
+__global__ void __launch_bounds__(kRowThreads) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
+                                                              float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + P.W;
@@ -163,80 +319,107 @@ __global__ void __launch_bounds__(256) k_fft_rows(const uint8_t* __restrict__ rg
     const uint8_t* pa = base + (size_t)ra * P.W * 3;
     const uint8_t* pb = base + (size_t)rb * P.W * 3;
     for (int x = threadIdx.x; x < P.W; x += blockDim.x) {
-        const int ga = 299 * (int)__ldg(pa + 3 * x) + 587 * (int)__ldg(pa + 3 * x + 1) + 114 * (int)__ldg(pa + 3 * x + 2);
-        int gb = 127500;
-        if (has_b) gb = 299 * (int)__ldg(pb + 3 * x) + 587 * (int)__ldg(pb + 3 * x + 1) + 114 * (int)__ldg(pb + 3 * x + 2);
-        bufA[x] = make_float2((float)(ga - 127500), (float)(gb - 127500));
+        const int ga = gray_num(pa + 3 * x);
+        const int gb = has_b ? gray_num(pb + 3 * x) : PHD_GRAY_BIAS;
+        bufA[x] = make_float2((float)(ga - PHD_GRAY_BIAS), (float)(gb - PHD_GRAY_BIAS));
     }
     __syncthreads();
-    const float2* z = fft_run(pl, bufA, bufB, 1, 0);
-    float2* oa = spec + ((size_t)img * P.H + ra) * P.fw;
-    float2* ob = spec + ((size_t)img * P.H + rb) * P.fw;
+    const float2* z = fft_run_rt(pl, bufA, bufB, 1, 0);
+    float2* out = specT + (size_t)img * P.fw * P.Hp;
     for (int k = threadIdx.x; k < P.fw; k += blockDim.x) {
         const int kc = k == 0 ? 0 : P.W - k;
-        const float2 zk = z[k];
-        const float2 zc = make_float2(z[kc].x, -z[kc].y);
-        oa[k] = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-        if (has_b) ob[k] = make_float2(0.5f * (zk.y - zc.y), -0.5f * (zk.x - zc.x));
+        const float2 zk = z[k], zc = z[kc];
+        float2* o = out + (size_t)k * P.Hp + ra;
+        o[0] = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+        if (has_b) o[1] = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Column pass + blur binning: one CTA per tile of TC adjacent spectrum columns.
-template <bool WRITE_POWER>
-__global__ void __launch_bounds__(256) k_fft_cols_blur(DevParams P, FftPlan pl, int TC,
-                                                       const float2* __restrict__ spec,
-                                                       const u16* __restrict__ binmap,
-                                                       const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
-                                                       u32* __restrict__ maxpow, float* __restrict__ power_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// mbarrier / bulk-copy helpers (PTX; SASS shows UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Epilogue shared by both column kernels.  res: transformed columns in shared memory (column c at res + c*cs);
+// map: bin ids of the same columns (shared or global, column c at map + c*ms).
+template <bool WRITE_POWER, int SEG>
+__device__ __forceinline__ void cols_epilogue(const DevParams& P, int img, int x0, int ncol, const float2* res, int cs,
+                                              const u16* map, int ms, const ImageAcc* __restrict__ iacc,
+                                              u32* bin_lo, u32* bin_hi, float* sh_max, u64* __restrict__ binsum,
+                                              u32* __restrict__ maxpow, float* __restrict__ power_out) {
     const int H = P.H;
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);
-    float2* bufB = bufA + (size_t)TC * H;
-    u32* bin_lo = reinterpret_cast<u32*>(bufB + (size_t)TC * H);
-    u32* bin_hi = bin_lo + P.nbins;
-    __shared__ float sh_max[8];
-
-    const int img = blockIdx.y;
-    const int x0 = blockIdx.x * TC;
-    const int ncol = min(TC, P.fw - x0);
-    const float2* src = spec + (size_t)img * H * P.fw;
-    if (!WRITE_POWER)
-        for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
-    for (int idx = threadIdx.x; idx < H * TC; idx += blockDim.x) {
-        const int k = idx / TC, c = idx - k * TC;
-        bufA[(size_t)c * H + k] = c < ncol ? src[(size_t)k * P.fw + x0 + c] : make_float2(0.f, 0.f);
-    }
-    __syncthreads();
-    const float2* res = fft_run(pl, bufA, bufB, ncol, H);
-
     const float inv_scale2 = (float)(1.0 / (255000.0 * 255000.0));
+    const int segs = (H + SEG - 1) / SEG;
     float mymax = 0.f;
-    for (int idx = threadIdx.x; idx < H * ncol; idx += blockDim.x) {
-        const int k = idx / ncol, c = idx - k * ncol;
+    for (int task = threadIdx.x; task < ncol * segs; task += blockDim.x) {
+        const int c = task / segs, k0 = (task - c * segs) * SEG;
         const int x = x0 + c;
-        const float2 v = res[(size_t)c * H + k];
-        float p = (v.x * v.x + v.y * v.y) * inv_scale2;
-        if (WRITE_POWER) {
-            power_out[((size_t)img * H + k) * P.fw + x] = p;
-        } else {
-            if (x == 0 && k == 0) {
-                // DC: sum(gray - avg) from the exact channel sums (interface.c:78, blur_profile.c:233-238)
-                const ImageAcc a = iacc[img];
-                const double np = (double)P.npx;
-                const double avg = ((double)a.sum[0] / 255.0 / np + (double)a.sum[1] / 255.0 / np +
-                                    (double)a.sum[2] / 255.0 / np) / 3.0;
-                const double gsum = (299.0 * (double)a.sum[0] + 587.0 * (double)a.sum[1] + 114.0 * (double)a.sum[2]) / 255000.0;
-                const double dc = gsum - np * avg;
-                p = (float)(dc * dc);
+        int run_bin = -1;
+        u32 run_sum = 0;
+#pragma unroll
+        for (int i = 0; i < SEG; i++) {
+            const int k = k0 + i;
+            if (k < H) {
+                const float2 v = res[c * cs + k];
+                float p = (v.x * v.x + v.y * v.y) * inv_scale2;
+                if (WRITE_POWER) {
+                    power_out[((size_t)img * H + k) * P.fw + x] = p;
+                } else {
+                    if (x == 0 && k == 0) {
+                        // DC: sum(gray - avg) from the exact channel sums (interface.c:78, blur_profile.c:233-238)
+                        const ImageAcc a = iacc[img];
+                        const double np = (double)P.npx;
+                        const double avg = ((double)a.sum[0] / 255.0 / np + (double)a.sum[1] / 255.0 / np +
+                                            (double)a.sum[2] / 255.0 / np) / 3.0;
+                        const double gsum = (299.0 * (double)a.sum[0] + 587.0 * (double)a.sum[1] + 114.0 * (double)a.sum[2]) / 255000.0;
+                        const double dc = gsum - np * avg;
+                        p = (float)(dc * dc);
+                    }
+                    mymax = fmaxf(mymax, p);
+                    if (p >= 1.0f) {
+                        const u32 q = (u32)__float2int_rn(__logf(p) * (float)(1 << PHD_LN_SHIFT));
+                        const int bin = map[c * ms + k];
+                        if (bin != run_bin) {
+                            if (run_sum) {
+                                atomicAdd(&bin_lo[run_bin], run_sum & 0x1fffu);
+                                atomicAdd(&bin_hi[run_bin], run_sum >> 13);
+                            }
+                            run_bin = bin;
+                            run_sum = 0;
+                        }
+                        run_sum += q;
+                    }
+                }
             }
-            mymax = fmaxf(mymax, p);
-            if (p >= 1.0f) {
-                const u32 q = (u32)__float2int_rn(logf(p) * (float)(1 << PHD_LN_SHIFT));
-                const int bin = binmap[(size_t)k * P.fw + x];
-                atomicAdd(&bin_lo[bin], q & 0x1fffu);
-                atomicAdd(&bin_hi[bin], q >> 13);
-            }
+        }
+        if (!WRITE_POWER && run_sum) {
+            atomicAdd(&bin_lo[run_bin], run_sum & 0x1fffu);
+            atomicAdd(&bin_hi[run_bin], run_sum >> 13);
         }
     }
     if (WRITE_POWER) return;
@@ -256,6 +439,73 @@ __global__ void __launch_bounds__(256) k_fft_cols_blur(DevParams P, FftPlan pl, 
     }
 }
 
+// Columns, specialised: NB contiguous columns per CTA, staged by the bulk-copy engine.
+// Requires Hp == N (H % 4 == 0) so that columns and bin-map slices are 16-byte multiples.
+template <int N, int R0, int R1, int R2, int R3, int NB, bool WRITE_POWER>
+__global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float2* __restrict__ tw,
+                                                        const float2* __restrict__ specT,
+                                                        const u16* __restrict__ binmapT,
+                                                        const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
+                                                        u32* __restrict__ maxpow, float* __restrict__ power_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);
+    float2* bufB = bufA + NB * N;
+    u16* smap = reinterpret_cast<u16*>(bufB + NB * N);
+    u32* bin_lo = reinterpret_cast<u32*>(smap + NB * N);
+    u32* bin_hi = bin_lo + P.nbins;
+    __shared__ __align__(8) u64 bar;
+    __shared__ float sh_max[kColThreads / 32];
+
+    const int img = blockIdx.y;
+    const int x0 = blockIdx.x * NB;
+    const int ncol = min(NB, P.fw - x0);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        const u32 cbytes = (u32)(ncol * N * sizeof(float2)), mbytes = (u32)(ncol * N * sizeof(u16));
+        mbar_expect_tx(&bar, cbytes + mbytes);
+        bulk_g2s(bufA, specT + ((size_t)img * P.fw + x0) * N, cbytes, &bar);
+        bulk_g2s(smap, binmapT + (size_t)x0 * N, mbytes, &bar);
+    }
+    if (!WRITE_POWER)
+        for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
+    __syncthreads();  // barrier init visible to every waiter
+    mbar_wait(&bar, 0);
+    const float2* res = fft_run_t<N, R0, R1, R2, R3>(bufA, bufB, tw, ncol, N);
+    constexpr int SEG = (NB * N + kColThreads - 1) / kColThreads;
+    cols_epilogue<WRITE_POWER, SEG>(P, img, x0, ncol, res, N, smap, N, iacc, bin_lo, bin_hi, sh_max, binsum, maxpow,
+                                    power_out);
+}
+
+// Columns, generic: runtime radix plan, plain loads, bin ids read from global memory.
+template <bool WRITE_POWER>
+__global__ void __launch_bounds__(kColThreads) k_cols_generic(DevParams P, FftPlan pl, int TC,
+                                                              const float2* __restrict__ specT,
+                                                              const u16* __restrict__ binmapT,
+                                                              const ImageAcc* __restrict__ iacc,
+                                                              u64* __restrict__ binsum, u32* __restrict__ maxpow,
+                                                              float* __restrict__ power_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = P.H, Hp = P.Hp;
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);
+    float2* bufB = bufA + (size_t)TC * Hp;
+    u32* bin_lo = reinterpret_cast<u32*>(bufB + (size_t)TC * Hp);
+    u32* bin_hi = bin_lo + P.nbins;
+    __shared__ float sh_max[kColThreads / 32];
+
+    const int img = blockIdx.y;
+    const int x0 = blockIdx.x * TC;
+    const int ncol = min(TC, P.fw - x0);
+    const float2* src = specT + ((size_t)img * P.fw + x0) * Hp;
+    if (!WRITE_POWER)
+        for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
+    for (int idx = threadIdx.x; idx < ncol * Hp; idx += blockDim.x) bufA[idx] = src[idx];
+    __syncthreads();
+    const float2* res = fft_run_rt(pl, bufA, bufB, ncol, Hp);
+    (void)H;
+    cols_epilogue<WRITE_POWER, 8>(P, img, x0, ncol, res, Hp, binmapT + (size_t)x0 * Hp, Hp, iacc, bin_lo, bin_hi,
+                                  sh_max, binsum, maxpow, power_out);
+}
+
 // ------------------------------------------------------------------------------------------
 __device__ int newton_isqrt(double val) {
     if (val == 0.0) return 0;
@@ -267,11 +517,12 @@ __device__ int newton_isqrt(double val) {
     }
 }
 
-__global__ void k_bin_map(int W, int H, int nr, int na, u16* __restrict__ map, int* __restrict__ counts) {
+// Bin id of spectrum element (row k, column x), stored transposed: map[x*Hp + k].
+__global__ void k_bin_map(int W, int H, int Hp, int nr, int na, u16* __restrict__ map, int* __restrict__ counts) {
     const int fw = W / 2 + 1;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)fw * H) return;
-    const int k = (int)(i / fw), x = (int)(i - (long long)k * fw);
+    const int x = (int)(i / H), k = (int)(i - (long long)x * H);
     const int hb = H / 2 + (H % 2 == 1 ? 1 : 0);
     // rows k >= H - hb are written last by the reference loop (bottom half overwrites the middle row)
     int y;
@@ -287,23 +538,55 @@ __global__ void k_bin_map(int W, int H, int nr, int na, u16* __restrict__ map, i
     if (rb == nr) rb--;
     int bin = pb * nr + rb;
     bin = min(max(bin, 0), na * nr - 1);
-    map[i] = (u16)bin;
+    map[(size_t)x * Hp + k] = (u16)bin;
     atomicAdd(&counts[bin], 1);
+}
+
+// ---- dispatch tables of the specialised shapes -------------------------------------------------
+template <int N, int R0, int R1, int R2, int R3>
+void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
+    const size_t smem = (size_t)4 * N * sizeof(float2);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    k_rows_t<N, R0, R1, R2, R3><<<dim3(P.H / 4, nimg), kRowThreads, smem, st>>>(rgb, P, tw, specT);
+}
+
+template <int N, int R0, int R1, int R2, int R3, int NB>
+void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
+                   Workspace& ws, float* power_out, cudaStream_t st) {
+    const size_t smem = (size_t)2 * NB * N * sizeof(float2) + (size_t)NB * N * sizeof(u16) + (size_t)2 * P.nbins * sizeof(u32);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_cols_t<N, R0, R1, R2, R3, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_cols_t<N, R0, R1, R2, R3, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    dim3 grid((P.fw + NB - 1) / NB, nimg);
+    if (power_out)
+        k_cols_t<N, R0, R1, R2, R3, NB, true><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out);
+    else
+        k_cols_t<N, R0, R1, R2, R3, NB, false><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr);
 }
 
 }  // namespace
 
 int phd_fft_plan_factors(int n, int* fac, int* nfac) {
     int rem = n, k = 0;
-    while (rem % 4 == 0) { fac[k++] = 4; rem /= 4; }
-    while (rem % 2 == 0) { fac[k++] = 2; rem /= 2; }
-    for (int q = 3; rem > 1; q += 2) {
-        while (rem % q == 0) {
-            if (q > 31 || k >= PHD_MAX_FACTORS) return 1;  // large prime factor: not covered yet
-            fac[k++] = q;
-            rem /= q;
+    // an odd radix first keeps the stride-R stores of the first pass conflict free
+    int odd[PHD_MAX_FACTORS], no = 0, tmp = n;
+    for (int q = 3; tmp > 1 && q <= tmp; q += 2)
+        while (tmp % q == 0) {
+            if (q > 31 || no >= PHD_MAX_FACTORS) return 1;  // large prime factor: not covered yet
+            odd[no++] = q;
+            tmp /= q;
         }
-    }
+    for (int i = 0; i < no; i++) { fac[k++] = odd[i]; rem /= odd[i]; }
+    while (rem % 4 == 0) { if (k >= PHD_MAX_FACTORS) return 1; fac[k++] = 4; rem /= 4; }
+    while (rem % 2 == 0) { if (k >= PHD_MAX_FACTORS) return 1; fac[k++] = 2; rem /= 2; }
+    if (rem != 1) return 1;
     *nfac = k;
     return 0;
 }
@@ -312,18 +595,28 @@ void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st) {
     k_twiddles<<<(n + 255) / 256, 256, 0, st>>>(dev_tw, n);
 }
 
-int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* spec,
+static bool rows_fast_ok(const DevParams& P) {
+    return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && (P.W == 1920 || P.W == 3840 || P.W == 6000);
+}
+
+int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* specT,
                         cudaStream_t st, int* launches) {
+    *launches += 1;
+    if (rows_fast_ok(P)) {
+        switch (P.W) {
+            case 1920: launch_rows_t<1920, 15, 8, 16, 1>(rgb, P, nimg, row.tw, specT, st); return 0;
+            case 3840: launch_rows_t<3840, 15, 16, 16, 1>(rgb, P, nimg, row.tw, specT, st); return 0;
+            case 6000: launch_rows_t<6000, 15, 25, 16, 1>(rgb, P, nimg, row.tw, specT, st); return 0;
+        }
+    }
     const size_t smem = (size_t)P.W * 2 * sizeof(float2);
     if (smem > 200 * 1024) return 1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_rows_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    dim3 grid((P.H + 1) / 2, nimg);
-    k_fft_rows<<<grid, 256, smem, st>>>(rgb, P, row, spec);
-    *launches += 1;
+    k_rows_generic<<<dim3((P.H + 1) / 2, nimg), kRowThreads, smem, st>>>(rgb, P, row, specT);
     return 0;
 }
 
@@ -331,33 +624,41 @@ size_t phd_fft_cols_smem(const DevParams& P, int* tile_cols) {
     const size_t bins = (size_t)2 * P.nbins * sizeof(u32);
     const size_t budget = 200 * 1024;
     int tc = 8;
-    while (tc > 1 && (size_t)tc * P.H * 2 * sizeof(float2) + bins > budget) tc >>= 1;
+    while (tc > 1 && (size_t)tc * P.Hp * 2 * sizeof(float2) + bins > budget) tc >>= 1;
     *tile_cols = tc;
-    return (size_t)tc * P.H * 2 * sizeof(float2) + bins;
+    return (size_t)tc * P.Hp * 2 * sizeof(float2) + bins;
 }
 
-int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* spec, const u16* binmap,
+int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* specT, const u16* binmapT,
                              Workspace& ws, float* power_out, cudaStream_t st, int* launches) {
+    *launches += 1;
+    if (P.Hp == P.H) {
+        switch (P.H) {
+            case 1080: launch_cols_t<1080, 15, 8, 9, 1, 4>(P, nimg, col.tw, specT, binmapT, ws, power_out, st); return 0;
+            case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.tw, specT, binmapT, ws, power_out, st); return 0;
+            case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.tw, specT, binmapT, ws, power_out, st); return 0;
+        }
+    }
     int tc;
     const size_t smem = phd_fft_cols_smem(P, &tc);
     if (smem > 200 * 1024) return 1;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_fft_cols_blur<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_fft_cols_blur<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_cols_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_cols_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     dim3 grid((P.fw + tc - 1) / tc, nimg);
     if (power_out)
-        k_fft_cols_blur<true><<<grid, 256, smem, st>>>(P, col, tc, spec, binmap, ws.iacc, ws.binsum, ws.maxpow, power_out);
+        k_cols_generic<true><<<grid, kColThreads, smem, st>>>(P, col, tc, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out);
     else
-        k_fft_cols_blur<false><<<grid, 256, smem, st>>>(P, col, tc, spec, binmap, ws.iacc, ws.binsum, ws.maxpow, nullptr);
-    *launches += 1;
+        k_cols_generic<false><<<grid, kColThreads, smem, st>>>(P, col, tc, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr);
     return 0;
 }
 
-void phd_launch_bin_map(int W, int H, int nr, int na, u16* map_dev, int* counts_dev, cudaStream_t st) {
+void phd_launch_bin_map(int W, int H, int Hp, int nr, int na, u16* map_dev, int* counts_dev, cudaStream_t st) {
     const long long n = (long long)(W / 2 + 1) * H;
     cudaMemsetAsync(counts_dev, 0, sizeof(int) * na * nr, st);
-    k_bin_map<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, H, nr, na, map_dev, counts_dev);
+    cudaMemsetAsync(map_dev, 0, sizeof(u16) * (size_t)(W / 2 + 1) * Hp, st);
+    k_bin_map<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, H, Hp, nr, na, map_dev, counts_dev);
 }

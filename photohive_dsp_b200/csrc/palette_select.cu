@@ -9,6 +9,8 @@
 // rather than replaced by "a sort".  The tie path follows the behaviour of the shipped -O0
 // binary: the first tied parent always wins (get_distance_pixel_to_parent has no return value,
 // :303-311) and pixels beyond the tail node's free room are dropped except the last (:435-440).
+#include <limits.h>
+
 #include "phd_internal.h"
 
 namespace {
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                                                         GroupPlan* __restrict__ plan_g, int* __restrict__ pal_n,
                                                         int* __restrict__ parent_ids, int* __restrict__ tie_list,
                                                         int* __restrict__ tie_n, int* __restrict__ tie_groups,
-                                                        long long* __restrict__ dropped) {
+                                                        long long* __restrict__ dropped, SlotAcc* __restrict__ sacc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = P.T, tid = threadIdx.x, img = blockIdx.x;
     int* n = reinterpret_cast<int*>(smem_raw);       // [T] pixel counts
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     int* pend = fill + T;                            // [T] per parent slot: group whose last pixel is pending
     int* take = pend + T;                            // [T] tie groups: pixels accepted from the front
     int* keep = take + T;                            // [T] tie groups: last pixel survives
+    int* scnt = keep + T;                            // [T] per parent slot: pixels that end up in it
     __shared__ int sh_N, sh_nt;
 
     const double* gh = centres;
@@ -75,16 +78,50 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     }
     __syncthreads();
 
+    // Fast path: when every pair of saliencies is either equal or at least 1 apart and nothing can overflow
+    // the float->int truncation, the reference's comparator is a strict weak order and its insertion sort
+    // is the stable descending sort -- computed here as a parallel rank sort.  Otherwise (differences in
+    // (0,1), |values| >= 2^30, NaN) thread 0 replays the insertion sort step by step.
+    int* rank = first;  // scratch, reused below
+    for (int g = tid; g < T; g += blockDim.x) {
+        const float sg = sal[g];
+        int r = 0;
+        for (int o = 0; o < T; o++) {
+            const float so = sal[o];
+            r += (so > sg) || (so == sg && o < g);
+        }
+        rank[g] = r;
+    }
+    __syncthreads();
+    for (int g = tid; g < T; g += blockDim.x) ids[rank[g]] = g;
+    __syncthreads();
+    int ok = 1;
+    for (int i = tid; i < T; i += blockDim.x) {
+        const float a = sal[ids[i]];
+        if (!(fabsf(a) < 1073741824.0f)) ok = 0;
+        if (i + 1 < T) {
+            const float d = __fsub_rn(a, sal[ids[i + 1]]);
+            if (!(d == 0.0f || d >= 1.0f)) ok = 0;
+        }
+    }
+    const int safe = __syncthreads_and(ok);
+    if (!safe) {
+        for (int g = tid; g < T; g += blockDim.x) ids[g] = g;
+        __syncthreads();
+    }
+
     if (tid == 0) {
-        // insertion sort exactly as custom_sort walks it
-        for (int i = 1; i < T; i++) {
-            for (int j = i; j > 0; j--) {
-                const int a = ids[j], b = ids[j - 1];
-                if (trunc_f2i_x86(__fsub_rn(sal[b], sal[a])) < 0) {
-                    ids[j] = b;
-                    ids[j - 1] = a;
-                } else
-                    break;
+        if (!safe) {
+            // insertion sort exactly as custom_sort walks it
+            for (int i = 1; i < T; i++) {
+                for (int j = i; j > 0; j--) {
+                    const int a = ids[j], b = ids[j - 1];
+                    if (trunc_f2i_x86(__fsub_rn(sal[b], sal[a])) < 0) {
+                        ids[j] = b;
+                        ids[j - 1] = a;
+                    } else
+                        break;
+                }
             }
         }
         int goal = (int)((double)P.hpx * P.coverage);
@@ -102,6 +139,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
             const int pn = n[ids[j]];
             fill[j] = pn > 0 ? ((pn - 1) % P.L) + 1 : 0;
             pend[j] = -1;
+            scnt[j] = pn;
         }
     }
     __syncthreads();
@@ -136,17 +174,20 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                 const int tk = room < n[g] ? room : n[g];
                 take[g] = tk;
                 fill[f] += tk;
+                scnt[f] += tk;
                 if (tk < n[g]) {
-                    if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; }
+                    if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; scnt[f] -= 1; }
                     pend[f] = g;
                     keep[g] = 1;
+                    scnt[f] += 1;
                     drop += n[g] - tk - 1;
                 }
                 tie_list[(size_t)img * T + nt++] = g;
             } else {
                 take[g] = -1;
-                if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; pend[f] = -1; }
+                if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; pend[f] = -1; scnt[f] -= 1; }
                 fill[f] = ((n[g] - 1) % P.L) + 1;
+                scnt[f] += n[g];
             }
         }
         sh_nt = nt;
@@ -188,20 +229,23 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
         }
         plan_g[(size_t)img * T + g] = gp;
     }
-    for (int j = tid; j < T; j += blockDim.x) parent_ids[(size_t)img * T + j] = j < N ? ids[j] : -1;
+    for (int j = tid; j < T; j += blockDim.x) {
+        parent_ids[(size_t)img * T + j] = j < N ? ids[j] : -1;
+        if (j < N) sacc[(size_t)img * T + j].cnt = (u64)scnt[j];
+    }
 }
 
 }  // namespace
 
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
                                cudaStream_t st, int* launches) {
-    const size_t smem = (size_t)P.T * 10 * sizeof(int);
+    const size_t smem = (size_t)P.T * 11 * sizeof(int);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_palette_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.hist, ws.counts_chunk, ws.plan, ws.pal_n,
-                                              ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped);
+                                              ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped, ws.sacc);
     *launches += 1;
 }

@@ -17,7 +17,7 @@
 
 // Fixed-point scales of the integer accumulators (all sums are exact integers => order independent).
 #define PHD_S_SHIFT 30        // saturation: s * 2^30
-#define PHD_T_SHIFT 21        // wrapped hue: t * 2^21 (t <= 360)
+#define PHD_T_SHIFT 22        // hue and wrapped hue: degrees * 2^22 (< 2^31)
 #define PHD_LN_SHIFT 20       // ln(power): value * 2^20 (value < 2^6)
 
 typedef unsigned long long u64;
@@ -27,6 +27,7 @@ typedef unsigned short u16;
 // Everything a kernel needs to know about the job; passed by value.
 struct DevParams {
     int W, H, fw;        // full image, fw = W/2+1 spectrum columns
+    int Hp;              // column pitch of the transposed spectrum / bin map: H rounded up to a multiple of 4
     int dw, dh, ds;      // HSV (possibly downsampled) image and the rate
     long long npx, hpx;  // W*H and dw*dh
     int nchunks;         // ceil(hpx / PHD_CHUNK)
@@ -92,7 +93,7 @@ struct Workspace {
     int* tie_groups;     // [cap]
     long long* dropped;  // [cap]
     SlotAcc* sacc;       // [cap][T]
-    float2* spec;        // [cap][H][fw]
+    float2* spec;        // [fft cap][fw][Hp]  row-transformed half spectrum, transposed
     u64* binsum;         // [cap][nbins]
     u32* maxpow;         // [cap] float bits
     SharpAcc* sharp;     // [cap][max_boxes]
@@ -100,13 +101,16 @@ struct Workspace {
 };
 
 // ---- launchers (each in its own .cu) --------------------------------------------------------
-void phd_launch_frontend(const uint8_t* rgb, const DevParams& P, int nimg, const double* centres, Workspace& ws,
-                         cudaStream_t st, int* launches);
+void phd_launch_frontend(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* pal_tables,
+                         Workspace& ws, cudaStream_t st, int* launches);
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
                                cudaStream_t st, int* launches);
 void phd_launch_palette_accumulate(const uint8_t* rgb, const DevParams& P, int nimg, const double* centres,
-                                   Workspace& ws, cudaStream_t st, int* launches);
-void phd_launch_group_sweep(const DevParams& P, u16* out_dev, cudaStream_t st);
+                                   const unsigned char* pal_tables, Workspace& ws, cudaStream_t st, int* launches);
+void phd_launch_group_sweep(const DevParams& P, const unsigned char* pal_tables, bool fast, u16* out_dev,
+                            cudaStream_t st);
+void phd_launch_build_pal_tables(const DevParams& P, unsigned char* tables_dev, int* ok_dev, cudaStream_t st);
+size_t phd_pal_tables_size(int sp);
 
 int phd_fft_plan_factors(int n, int* fac, int* nfac);  // 0 ok, nonzero unsupported
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st);
@@ -114,7 +118,7 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
                         cudaStream_t st, int* launches);
 int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* spec, const u16* binmap,
                              Workspace& ws, float* power_out, cudaStream_t st, int* launches);
-void phd_launch_bin_map(int W, int H, int nr, int na, u16* map_dev, int* counts_dev, cudaStream_t st);
+void phd_launch_bin_map(int W, int H, int Hp, int nr, int na, u16* map_dev, int* counts_dev, cudaStream_t st);
 
 void phd_launch_sharpness(const uint8_t* rgb, const DevParams& P, int nimg, int max_w, int max_h, Workspace& ws,
                           cudaStream_t st, int* launches);

@@ -28,6 +28,7 @@ struct ParamTables {
     phd_params p;
     double* centres = nullptr;  // device [3*T]: group centre h, s, v
     float* sv_f = nullptr;      // device [T]: (float)(s*v) of the centre
+    unsigned char* pal = nullptr;  // device: value / saturation / reciprocal tables of hsv_fast.cuh
 };
 
 }  // namespace
@@ -47,6 +48,8 @@ struct phd_context {
     unsigned char* d_records = nullptr;
     size_t d_records_bytes = 0;
     std::vector<cudaEvent_t> events;
+    std::vector<int> spans;  // (stage, start event index, end event index) triples of the last call
+    size_t events_used = 0;
     float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int last_launches = 0;
     char err[512] = {0};
@@ -101,6 +104,8 @@ int check_params(phd_context* ctx, const phd_params* p, int max_boxes) {
     const long long T = (long long)p->h_partitions * p->s_partitions * p->v_partitions + p->v_partitions + 1;
     if (T > PHD_MAX_GROUPS) return fail(ctx, PHD_E_BAD_PARAMS, "palette grid larger than PHD_MAX_GROUPS groups");
     if (p->h_partitions > 360) return fail(ctx, PHD_E_BAD_PARAMS, "h_partitions > 360 gives a zero-width hue bin");
+    if (!(p->black_thresh >= 0.0 && p->black_thresh < 1.0 && p->gray_thresh >= 0.0 && p->gray_thresh < 1.0))
+        return fail(ctx, PHD_E_BAD_PARAMS, "black_thresh and gray_thresh must lie in [0, 1)");
     if (p->radius_partitions <= 0 || p->angle_partitions <= 1 ||
         (long long)p->radius_partitions * p->angle_partitions > PHD_MAX_BINS || p->angle_partitions > 180)
         return fail(ctx, PHD_E_BAD_PARAMS, "radius/angle partitions out of range");
@@ -113,6 +118,7 @@ int check_params(phd_context* ctx, const phd_params* p, int max_boxes) {
 void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_boxes, size_t stride, int aligned16) {
     memset(&P, 0, sizeof(P));
     P.W = W; P.H = H; P.fw = W / 2 + 1;
+    P.Hp = (H + 3) / 4 * 4;
     P.ds = p.downsample_rate > 1 ? p.downsample_rate : 1;
     P.dw = P.ds > 1 ? W / P.ds : W;
     P.dh = P.ds > 1 ? H / P.ds : H;
@@ -179,7 +185,22 @@ int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
     CUDA_TRY(ctx, cudaMalloc(&t.sv_f, sizeof(float) * T));
     CUDA_TRY(ctx, cudaMemcpyAsync(t.centres, c.data(), sizeof(double) * 3 * T, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(t.sv_f, sv.data(), sizeof(float) * T, cudaMemcpyHostToDevice, ctx->stream));
+    // fast-path tables, built on the device with the exact arithmetic
+    DevParams P;
+    fill_dev_params(P, p, 1024, 1024, 0, 0, 0);
+    int* ok_dev = nullptr;
+    int ok = 1;
+    CUDA_TRY(ctx, cudaMalloc(&t.pal, phd_pal_tables_size(sp)));
+    CUDA_TRY(ctx, cudaMalloc(&ok_dev, sizeof(int)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ok_dev, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    phd_launch_build_pal_tables(P, t.pal, ok_dev, ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(&ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ok_dev);
+    if (!ok) {
+        cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.pal);
+        return fail(ctx, PHD_E_UNSUPPORTED, "saturation classes are not monotone for these thresholds");
+    }
     ctx->tables.push_back(t);
     *out = &ctx->tables.back();
     return PHD_OK;
@@ -193,14 +214,15 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
     s.row.n = W; s.col.n = H;
     if (phd_fft_plan_factors(W, s.row.fac, &s.row.nfac) || phd_fft_plan_factors(H, s.col.fac, &s.col.nfac))
         return fail(ctx, PHD_E_UNSUPPORTED, "image side has a prime factor > 31: FFT length not supported by this build");
-    const size_t nspec = (size_t)(W / 2 + 1) * H;
+    const int Hp = (H + 3) / 4 * 4;
+    const size_t nspec = (size_t)(W / 2 + 1) * Hp;
     CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * W));
     CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * H));
     CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
     CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
     phd_fill_twiddles(s.tw_row, W, ctx->stream);
     phd_fill_twiddles(s.tw_col, H, ctx->stream);
-    phd_launch_bin_map(W, H, nr, na, s.binmap, s.bincount, ctx->stream);
+    phd_launch_bin_map(W, H, Hp, nr, na, s.binmap, s.bincount, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     s.row.tw = s.tw_row;
@@ -212,9 +234,9 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int ensure_workspace(phd_context* ctx, const DevParams& P, int cap) {
+int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft) {
     const size_t key[8] = {(size_t)cap, (size_t)P.T, (size_t)P.nchunks, (size_t)P.H, (size_t)P.fw,
-                           (size_t)P.nbins, (size_t)P.max_boxes, 0};
+                           (size_t)P.nbins, (size_t)P.max_boxes, (size_t)cap_fft};
     if (memcmp(key, ctx->ws_key, sizeof(key)) == 0 && ctx->ws.capacity == cap) return PHD_OK;
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
@@ -231,7 +253,7 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap) {
     CUDA_TRY(ctx, cudaMalloc(&w.tie_n, sizeof(int) * c));
     CUDA_TRY(ctx, cudaMalloc(&w.tie_groups, sizeof(int) * c));
     CUDA_TRY(ctx, cudaMalloc(&w.dropped, sizeof(long long) * c));
-    CUDA_TRY(ctx, cudaMalloc(&w.spec, sizeof(float2) * c * P.H * P.fw));
+    CUDA_TRY(ctx, cudaMalloc(&w.spec, sizeof(float2) * (size_t)cap_fft * P.Hp * P.fw));
     CUDA_TRY(ctx, cudaMalloc(&w.boxes, sizeof(int) * 4 * c * (P.max_boxes > 0 ? P.max_boxes : 1)));
     // zero-initialised accumulators, contiguous so one memset per sub-batch clears them
     size_t off = 0;
@@ -273,19 +295,35 @@ bool is_device_pointer(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-int pick_sub_batch(const DevParams& P, int n_images) {
+// Images per FFT sub-batch: the row-transformed spectra of one sub-batch should stay L2 resident
+// between the row and the column kernel (L2 is 126 MB on B200).
+int pick_fft_batch(const DevParams& P, int n_images) {
     const char* env = getenv("PHD_SUB_BATCH");
-    long long sub = 0;
-    if (env) sub = atoll(env);
+    long long sub = env ? atoll(env) : 0;
     if (sub <= 0) {
-        // keep the row-transformed spectra of one sub-batch around 128 MB (L2 is 126 MB on B200)
         const double per = (double)P.H * P.fw * sizeof(float2);
-        sub = (long long)(128.0 * 1024 * 1024 / per);
+        sub = (long long)(96.0 * 1024 * 1024 / per);
         if (sub < 1) sub = 1;
         if (sub > 64) sub = 64;
     }
     if (sub > n_images) sub = n_images;
     return (int)sub;
+}
+
+// Images per palette group (front end, parent selection, accumulation, sharpness, finalize): large, so the
+// one-CTA-per-image kernels fill the machine; bounded by the per-chunk histogram storage.
+int pick_palette_batch(const DevParams& P, int n_images, bool host_input) {
+    const char* env = getenv("PHD_PALETTE_BATCH");
+    long long pb = env ? atoll(env) : 0;
+    if (pb <= 0) {
+        pb = host_input ? 128 : 512;
+        const double per = (double)P.nchunks * P.T * sizeof(u16);
+        const long long cap = (long long)(1024.0 * 1024 * 1024 / per);
+        if (pb > cap) pb = cap;
+        if (pb < 1) pb = 1;
+    }
+    if (pb > n_images) pb = n_images;
+    return (int)pb;
 }
 
 enum { ST_FRONT = 1, ST_SELECT, ST_ACCUM, ST_ROWS, ST_COLS, ST_SHARP, ST_FINAL };
@@ -307,26 +345,32 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
     int rc;
     if ((rc = get_shape(ctx, W, H, P.nr, P.na, &shape)) != PHD_OK) return rc;
     if ((rc = get_tables(ctx, p, &tab)) != PHD_OK) return rc;
-    const int sub = pick_sub_batch(P, n_images);
-    if ((rc = ensure_workspace(ctx, P, sub)) != PHD_OK) return rc;
-    if (!input_on_device && (rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, dev_stride * sub)) != PHD_OK) return rc;
+    const int pb = pick_palette_batch(P, n_images, !input_on_device);
+    const int fb = pick_fft_batch(P, pb);
+    if ((rc = ensure_workspace(ctx, P, pb, fb)) != PHD_OK) return rc;
+    if (!input_on_device && (rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, dev_stride * pb)) != PHD_OK) return rc;
     int tc;
     if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
         return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
 
     cudaStream_t st = ctx->stream;
-    const int nsub = (n_images + sub - 1) / sub;
-    const size_t nev = 2 + (size_t)nsub * 8;
-    while (ctx->events.size() < nev) {
-        cudaEvent_t e;
-        CUDA_TRY(ctx, cudaEventCreate(&e));
-        ctx->events.push_back(e);
-    }
+    ctx->spans.clear();
+    ctx->events_used = 0;
+    auto mark = [&](int* idx) -> int {
+        if (ctx->events_used == ctx->events.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return 1;
+            ctx->events.push_back(e);
+        }
+        *idx = (int)ctx->events_used++;
+        return cudaEventRecord(ctx->events[*idx], st) != cudaSuccess;
+    };
+    auto span = [&](int stage, int a, int b) { ctx->spans.push_back(stage); ctx->spans.push_back(a); ctx->spans.push_back(b); };
     int launches = 0;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->events[0], st));
-    for (int sb = 0; sb < nsub; sb++) {
-        const int first = sb * sub;
-        const int n = (n_images - first < sub) ? (n_images - first) : sub;
+    int e_begin, e_end, e0, e1;
+    if (mark(&e_begin)) return fail(ctx, PHD_E_CUDA, "cudaEventRecord failed");
+    for (int first = 0; first < n_images; first += pb) {
+        const int n = (n_images - first < pb) ? (n_images - first) : pb;
         const uint8_t* d_in;
         if (input_on_device) d_in = rgb_host_or_dev + (size_t)first * image_stride;
         else {
@@ -350,42 +394,45 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
         // records carry padding bytes no kernel writes: clear them so equal images give equal bytes
         CUDA_TRY(ctx, cudaMemsetAsync(records_dev + (size_t)first * lay.record_bytes, 0, lay.record_bytes * (size_t)n, st));
-        cudaEvent_t* ev = &ctx->events[2 + (size_t)sb * 8];
-        CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
-        phd_launch_frontend(d_in, P, n, tab->centres, ctx->ws, st, &launches);
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_FRONT], st));
+        mark(&e0);
+        phd_launch_frontend(d_in, P, n, tab->pal, ctx->ws, st, &launches);
+        mark(&e1); span(ST_FRONT, e0, e1); e0 = e1;
         phd_launch_palette_select(P, n, tab->centres, tab->sv_f, ctx->ws, st, &launches);
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_SELECT], st));
-        phd_launch_palette_accumulate(d_in, P, n, tab->centres, ctx->ws, st, &launches);
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_ACCUM], st));
-        if (phd_launch_fft_rows(d_in, P, n, shape->row, ctx->ws.spec, st, &launches))
-            return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_ROWS], st));
-        if (phd_launch_fft_cols_blur(P, n, shape->col, ctx->ws.spec, shape->binmap, ctx->ws, nullptr, st, &launches))
-            return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_COLS], st));
+        mark(&e1); span(ST_SELECT, e0, e1); e0 = e1;
+        phd_launch_palette_accumulate(d_in, P, n, tab->centres, tab->pal, ctx->ws, st, &launches);
+        mark(&e1); span(ST_ACCUM, e0, e1); e0 = e1;
+        for (int f0 = 0; f0 < n; f0 += fb) {
+            const int nf = (n - f0 < fb) ? (n - f0) : fb;
+            Workspace sub = ctx->ws;  // accumulators of images f0.. of this group
+            sub.iacc += f0;
+            sub.binsum += (size_t)f0 * P.nbins;
+            sub.maxpow += f0;
+            if (phd_launch_fft_rows(d_in + (size_t)f0 * dev_stride, P, nf, shape->row, ctx->ws.spec, st, &launches))
+                return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
+            mark(&e1); span(ST_ROWS, e0, e1); e0 = e1;
+            if (phd_launch_fft_cols_blur(P, nf, shape->col, ctx->ws.spec, shape->binmap, sub, nullptr, st, &launches))
+                return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
+            mark(&e1); span(ST_COLS, e0, e1); e0 = e1;
+        }
         phd_launch_sharpness(d_in, P, n, max_w, max_h, ctx->ws, st, &launches);
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_SHARP], st));
+        mark(&e1); span(ST_SHARP, e0, e1); e0 = e1;
         phd_launch_finalize(P, n, tab->centres, shape->bincount, ctx->ws, lay,
                             records_dev + (size_t)first * lay.record_bytes, st, &launches);
-        CUDA_TRY(ctx, cudaEventRecord(ev[ST_FINAL], st));
+        mark(&e1); span(ST_FINAL, e0, e1);
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->events[1], st));
+    if (mark(&e_end)) return fail(ctx, PHD_E_CUDA, "cudaEventRecord failed");
+    span(0, e_begin, e_end);
     ctx->last_launches = launches;
     return PHD_OK;
 }
 
-int collect_timing(phd_context* ctx, int nsub) {
+int collect_timing(phd_context* ctx) {
     for (int i = 0; i < 8; i++) ctx->last_ms[i] = 0.f;
-    CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[0], ctx->events[0], ctx->events[1]));
-    for (int sb = 0; sb < nsub; sb++) {
-        cudaEvent_t* ev = &ctx->events[2 + (size_t)sb * 8];
-        for (int s = 1; s <= 7; s++) {
-            float ms = 0.f;
-            CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev[s - 1], ev[s]));
-            ctx->last_ms[s] += ms;
-        }
+    for (size_t i = 0; i + 2 < ctx->spans.size(); i += 3) {
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->events[ctx->spans[i + 1]], ctx->events[ctx->spans[i + 2]]));
+        ctx->last_ms[ctx->spans[i]] += ms;
     }
     return PHD_OK;
 }
@@ -468,7 +515,7 @@ void phd_context_destroy(phd_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->shapes) { cudaFree(s.tw_row); cudaFree(s.tw_col); cudaFree(s.binmap); cudaFree(s.bincount); }
-    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); }
+    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.pal); }
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
@@ -531,10 +578,7 @@ int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_images, int w
                                       ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
-    DevParams P;
-    fill_dev_params(P, *p, width, height, max_boxes, image_stride, 0);
-    const int sub = pick_sub_batch(P, n_images);
-    return collect_timing(ctx, (n_images + sub - 1) / sub);
+    return collect_timing(ctx);
 }
 
 int phd_last_timing(const phd_context* ctx, float ms[8]) {
@@ -601,7 +645,7 @@ Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_flat_lay
 // ---------------------------------------------------------------------------------------------
 // test hooks
 // ---------------------------------------------------------------------------------------------
-int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out) {
+static int group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out, bool fast) {
     if (!ctx || !out) return PHD_E_BAD_PARAMS;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_params(ctx, p, 0);
@@ -609,15 +653,20 @@ int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out) 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     DevParams P;
     fill_dev_params(P, *p, 1024, 1024, 0, 0, 0);
+    ParamTables* tab;
+    if ((rc = get_tables(ctx, *p, &tab)) != PHD_OK) return rc;
     u16* d;
     CUDA_TRY(ctx, cudaMalloc(&d, sizeof(u16) << 24));
-    phd_launch_group_sweep(P, d, ctx->stream);
+    phd_launch_group_sweep(P, tab->pal, fast, d, ctx->stream);
     cudaError_t e = cudaMemcpyAsync(out, d, sizeof(u16) << 24, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
     CUDA_TRY(ctx, e);
     return PHD_OK;
 }
+
+int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out) { return group_sweep(ctx, p, out, true); }
+int phd_debug_group_sweep_exact(phd_context* ctx, const phd_params* p, uint16_t* out) { return group_sweep(ctx, p, out, false); }
 
 int phd_debug_bin_map(phd_context* ctx, int width, int height, int nr, int na, uint16_t* map, int* counts) {
     if (!ctx) return PHD_E_BAD_PARAMS;
@@ -626,8 +675,14 @@ int phd_debug_bin_map(phd_context* ctx, int width, int height, int nr, int na, u
     ShapePlan* s;
     int rc = get_shape(ctx, width, height, nr, na, &s);
     if (rc != PHD_OK) return rc;
-    const size_t nspec = (size_t)(width / 2 + 1) * height;
-    if (map) CUDA_TRY(ctx, cudaMemcpy(map, s->binmap, sizeof(u16) * nspec, cudaMemcpyDeviceToHost));
+    if (map) {
+        // the device map is stored transposed ([x][k], pitch Hp); hand it back row major
+        const int fw = width / 2 + 1, Hp = (height + 3) / 4 * 4;
+        std::vector<u16> t((size_t)fw * Hp);
+        CUDA_TRY(ctx, cudaMemcpy(t.data(), s->binmap, sizeof(u16) * t.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < height; k++)
+            for (int x = 0; x < fw; x++) map[(size_t)k * fw + x] = t[(size_t)x * Hp + k];
+    }
     if (counts) CUDA_TRY(ctx, cudaMemcpy(counts, s->bincount, sizeof(int) * nr * na, cudaMemcpyDeviceToHost));
     return PHD_OK;
 }
@@ -644,7 +699,7 @@ int phd_debug_power_spectrum(phd_context* ctx, const uint8_t* rgb, int width, in
     ShapePlan* s;
     int rc = get_shape(ctx, width, height, P.nr, P.na, &s);
     if (rc != PHD_OK) return rc;
-    if ((rc = ensure_workspace(ctx, P, 1)) != PHD_OK) return rc;
+    if ((rc = ensure_workspace(ctx, P, 1, 1)) != PHD_OK) return rc;
     if ((rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, stride)) != PHD_OK) return rc;
     const size_t nspec = (size_t)P.fw * height;
     float* d_pow;
@@ -676,12 +731,12 @@ int phd_debug_group_counts(phd_context* ctx, const uint8_t* rgb, int width, int 
     fill_dev_params(P, *p, width, height, 0, stride, 1);
     ParamTables* tab;
     if ((rc = get_tables(ctx, *p, &tab)) != PHD_OK) return rc;
-    if ((rc = ensure_workspace(ctx, P, 1)) != PHD_OK) return rc;
+    if ((rc = ensure_workspace(ctx, P, 1, 1)) != PHD_OK) return rc;
     if ((rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, stride)) != PHD_OK) return rc;
     int launches = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_rgb, rgb, tight, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, ctx->stream));
-    phd_launch_frontend(ctx->d_rgb, P, 1, tab->centres, ctx->ws, ctx->stream, &launches);
+    phd_launch_frontend(ctx->d_rgb, P, 1, tab->pal, ctx->ws, ctx->stream, &launches);
     CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->ws.hist, sizeof(int) * P.T, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PHD_OK;

@@ -56,6 +56,8 @@ lib.phd_last_timing.restype = C.c_int
 lib.phd_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float * 8)]
 lib.phd_debug_group_sweep.restype = C.c_int
 lib.phd_debug_group_sweep.argtypes = [C.c_void_p, C.POINTER(phd_params), C.c_void_p]
+lib.phd_debug_group_sweep_exact.restype = C.c_int
+lib.phd_debug_group_sweep_exact.argtypes = [C.c_void_p, C.POINTER(phd_params), C.c_void_p]
 lib.phd_debug_bin_map.restype = C.c_int
 lib.phd_debug_bin_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 lib.phd_debug_power_spectrum.restype = C.c_int
@@ -66,4 +68,5 @@ lib.phd_debug_group_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
 EXPORTED = ["get_full_report_data", "free_full_report", "get_blur_profile_visual", "phd_default_params",
             "phd_context_create", "phd_context_destroy", "phd_last_error", "phd_flat_get_layout",
             "phd_get_reports_u8", "phd_flat_to_full_report", "phd_last_timing", "phd_debug_group_sweep",
+            "phd_debug_group_sweep_exact",
             "phd_debug_bin_map", "phd_debug_power_spectrum", "phd_debug_group_counts"]

@@ -6,36 +6,45 @@ implementation actually achieves is far tighter, and the tests pin that so regre
   integer outputs (palette N, parent order, angle/radius bin sizes, blur-vector angles, group counts,
   bin-id map, tie/dropped pixel counts)                        : exact
   palette percentages (count / P)                              : 1e-15 absolute (same integers, same division)
-  rgb_stats, average_saturation, sharpness, palette s and v    : 1e-9 relative
-  palette hue (degrees, circular quantity)                     : 1e-6 absolute
+  rgb_stats, sharpness, palette v (exact integer sums)         : 1e-9 relative
+  average_saturation, palette s (2^-30 fixed-point sums)       : 1e-8 relative
+  palette hue (degrees, circular; 2^-22 fixed-point sums)      : 2e-6 absolute
   blur-profile bins (FP32 transform vs the reference's FP64)   : 1e-4 relative with a 2e-6 absolute floor
   blur-vector magnitudes (k / nr as float)                     : exact
 """
 import numpy as np
 
 RTOL_STATS = 1e-9
-ATOL_HUE = 1e-6
+RTOL_SAT = 1e-8
+ATOL_HUE = 2e-6
 RTOL_BINS = 1e-4
 ATOL_BINS = 2e-6
 
 
 def rel_err(a, b, floor=1e-300):
+    """Relative error; positions where BOTH sides are NaN (e.g. 0/0 of an empty parent, which the reference
+    also produces) count as equal, a NaN on one side only as infinitely wrong."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
-    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+    both = np.isnan(a) & np.isnan(b)
+    with np.errstate(invalid="ignore"):
+        e = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    e = np.where(both, 0.0, e)
+    return np.where(np.isnan(e), np.inf, e)
 
 
 def assert_report_close(got, want, what=""):
     """got / want: oracle.binding.Report-like objects (numpy fields)."""
     assert np.all(rel_err(got.rgb_stats, want.rgb_stats, 1e-12) < RTOL_STATS), f"{what}: rgb_stats"
-    assert rel_err(got.average_saturation, want.average_saturation, 1e-12) < RTOL_STATS, f"{what}: average_saturation"
+    assert rel_err(got.average_saturation, want.average_saturation, 1e-12) < RTOL_SAT, f"{what}: average_saturation"
     assert len(got.palette_pct) == len(want.palette_pct), f"{what}: palette N {len(got.palette_pct)} != {len(want.palette_pct)}"
     assert np.max(np.abs(got.palette_pct - want.palette_pct), initial=0) <= 1e-15, f"{what}: palette percentages"
     if len(want.palette_pct):
-        dh = np.abs(got.palette_hsv[:, 0] - want.palette_hsv[:, 0])
-        dh = np.minimum(dh, 360 - dh)
+        dh = rel_err(got.palette_hsv[:, 0], want.palette_hsv[:, 0], 1.0) * np.maximum(np.abs(np.nan_to_num(want.palette_hsv[:, 0])), 1.0)
+        dh = np.minimum(dh, np.abs(360 - dh))
         assert np.max(dh) < ATOL_HUE, f"{what}: palette hue {np.max(dh)}"
-        assert np.all(rel_err(got.palette_hsv[:, 1:], want.palette_hsv[:, 1:], 1e-12) < RTOL_STATS), f"{what}: palette s/v"
+        assert np.all(rel_err(got.palette_hsv[:, 1], want.palette_hsv[:, 1], 1e-12) < RTOL_SAT), f"{what}: palette s"
+        assert np.all(rel_err(got.palette_hsv[:, 2], want.palette_hsv[:, 2], 1e-12) < RTOL_STATS), f"{what}: palette v"
     assert got.angle_bin_size == want.angle_bin_size and got.radius_bin_size == want.radius_bin_size, f"{what}: bin sizes"
     d = np.abs(got.blur_bins - want.blur_bins)
     assert np.all(d <= ATOL_BINS + RTOL_BINS * np.abs(want.blur_bins)), f"{what}: blur bins max abs {d.max()}"

@@ -19,10 +19,13 @@ FINE = dict(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.9
 @pytest.mark.parametrize("kw", [{}, FINE, dict(h_partitions=12, s_partitions=3, v_partitions=5, black_thresh=0.15, gray_thresh=0.2),
                                 dict(h_partitions=24, s_partitions=1, v_partitions=1)])
 def test_group_id_of_all_2pow24_colours(ctx, oracle, kw):
-    """the palette group of every 24-bit colour equals the reference arithmetic, bit for bit."""
-    got = ctx.debug_group_sweep(make_params(**kw))
+    """the palette group of every 24-bit colour equals the reference arithmetic, bit for bit --
+    both for the product path (integer fast path + FP64 edge path) and for the plain FP64 transcription."""
     want = oracle.group_sweep(omake(**kw))
-    assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} colours land in another group"
+    got = ctx.debug_group_sweep(make_params(**kw))
+    assert np.array_equal(got, want), f"fast path: {np.count_nonzero(got != want)} colours land in another group"
+    got = ctx.debug_group_sweep(make_params(**kw), exact=True)
+    assert np.array_equal(got, want), f"FP64 path: {np.count_nonzero(got != want)} colours land in another group"
 
 
 @pytest.mark.parametrize("shape", [(1920, 1080), (3840, 2160), (6000, 4000), (405, 357), (1080, 1920), (350, 350)])
@@ -69,6 +72,12 @@ def test_report_matches_reference_golden(ctx, oracle, golden, name):
     (700, 525, 1, dict(h_partitions=9, s_partitions=3, v_partitions=4, coverage_thresh=0.9)),
     (1024, 768, 0, dict(downsample_rate=2, radius_partitions=16, angle_partitions=36)),
     (3840, 2160, 1, {}),   # BASELINE config 2: 4K with four salient boxes
+    # saliencies closer than 1 apart: the truncating comparator calls them equal (insertion-sort replay)
+    (800, 600, 0, dict(quantity_weight=0.0, saturation_value_weight=1e-5)),
+    (800, 600, 1, dict(quantity_weight=1e-6, saturation_value_weight=1e-6, coverage_thresh=0.5)),
+    # saliencies beyond 2^31: the float->int conversion overflows to INT_MIN
+    (800, 600, 0, dict(quantity_weight=30000.0, saturation_value_weight=50000.0)),
+    (640, 480, 2, dict(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99, linked_list_size=3)),
 ])
 def test_report_matches_oracle(ctx, oracle, W, H, kind, kw):
     img = oracle.generate(kind, 1000 + W + kind, W, H)
@@ -184,12 +193,15 @@ def test_full_size_properties(ctx, oracle, W, H):
     counts = ctx.debug_group_counts(img, p)
     assert counts.sum() == P
     # exact channel statistics from integer sums
-    x = img.reshape(-1, 3).astype(np.float64) / 255.0
-    assert np.all(rel_err(b.rgb_stats[0, :3], x.mean(0)) < 1e-12)
-    assert np.all(rel_err(b.rgb_stats[0, 3:], x.std(0)) < 1e-9)
+    k = img.reshape(-1, 3).astype(np.int64)
+    s1, s2 = k.sum(0), (k * k).sum(0)   # exact integers; numpy's float mean over 8-24 M values drifts by 1e-11
+    assert np.all(rel_err(b.rgb_stats[0, :3], s1 / 255.0 / P) < 1e-13)
+    var = (s2 * P - s1 * s1).astype(np.float64) / (float(P) * P * 65025.0)
+    assert np.all(rel_err(b.rgb_stats[0, 3:], np.sqrt(var)) < 1e-12)
     # Parseval on the hand-written 2-D FFT: sum over the full spectrum of |X|^2 == W*H * sum x^2
     pw = ctx.debug_power_spectrum(img).astype(np.float64)
-    gnum = (299 * img[:, :, 0].astype(np.int64) + 587 * img[:, :, 1] + 114 * img[:, :, 2]) - 127500
+    i64 = img.astype(np.int64)
+    gnum = (299 * i64[:, :, 0] + 587 * i64[:, :, 1] + 114 * i64[:, :, 2]) - 127500
     energy = float(np.sum(gnum.astype(np.float64) ** 2)) / 255000.0 ** 2 * P
     wts = np.full(W // 2 + 1, 2.0)
     wts[0] = 1.0

@@ -40,7 +40,7 @@ def algo_bytes(w=W, h=H, box_area=0):
 # Algorithmic bytes per image of each kernel (its share of the figure above).
 def kernel_bytes():
     fw = W // 2 + 1
-    return {"frontend": 3 * W * H, "palette_accumulate": 3 * W * H, "fft_rows": 3 * W * H + 8 * H * fw,
+    return {"frontend": 3 * W * H, "fft_rows": 3 * W * H + 8 * H * fw,
             "fft_cols_blur": 8 * H * fw + 2 * H * fw}
 
 
@@ -280,7 +280,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_image": kb[dom],
-                         # 6 kernels per sub-batch (front end, select, accumulate, rows, cols+blur, finalize)
+                         # one launch of each kernel per (sub-)batch
                          "avg_launch_ms": per_kernel[dom] / max(launches // 6, 1)},
             "roofline_pipeline": {"algo_bytes_per_image": algo_bytes(), "achieved": pipe_achieved, "peak": peak,
                                   "unit": "GB/s", "frac": pipe_achieved / peak},

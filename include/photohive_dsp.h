@@ -210,8 +210,8 @@ PHD_API int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_image
 PHD_API Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_flat_layout* layout);
 
 /* Device timing of the last phd_get_reports_u8 call on ctx, in milliseconds (CUDA events on the
- * pipeline's own stream): [0] whole pipeline, [1] front end, [2] palette select, [3] palette
- * accumulate, [4] row FFT, [5] column FFT + blur binning, [6] sharpness, [7] finalize.
+ * pipeline's own stream): [0] whole pipeline, [1] front end, [2] palette select, [3] palette tie
+ * path, [4] row FFT, [5] column FFT + blur binning, [6] sharpness, [7] finalize.
  * Returns the number of kernel launches of that call. */
 PHD_API int phd_last_timing(const phd_context* ctx, float ms[8]);
 

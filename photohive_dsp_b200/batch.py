@@ -152,7 +152,7 @@ class Context:
     def last_timing(self):
         ms = (C.c_float * 8)()
         launches = lib.phd_last_timing(self._h, C.byref(ms))
-        names = ["total", "frontend", "palette_select", "palette_accumulate", "fft_rows", "fft_cols_blur",
+        names = ["total", "frontend", "palette_select", "palette_ties", "fft_rows", "fft_cols_blur",
                  "sharpness", "finalize"]
         return dict(zip(names, [float(x) for x in ms])), launches
 

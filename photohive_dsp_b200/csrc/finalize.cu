@@ -8,7 +8,7 @@
 // variance/mean of get_variance_sharpness (src/filtering.c:170-174).  One CTA per image.
 #include <math.h>
 
-#include "phd_internal.h"
+#include "cell_reduce.cuh"
 
 namespace {
 
@@ -23,7 +23,10 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
                                                   const int* __restrict__ bincount,
                                                   const ImageAcc* __restrict__ iacc, const int* __restrict__ pal_n,
                                                   const int* __restrict__ parent_ids,
-                                                  const SlotAcc* __restrict__ sacc, const u64* __restrict__ binsum,
+                                                  SlotAcc* sacc, const GroupPlan* __restrict__ plan_g,
+                                                  const int* __restrict__ tie_list, const int* __restrict__ tie_n,
+                                                  const u64* __restrict__ cells_tie_g,
+                                                  const u64* __restrict__ binsum,
                                                   const u32* __restrict__ maxpow, const SharpAcc* __restrict__ sharp,
                                                   const int* __restrict__ boxes, const int* __restrict__ tie_groups,
                                                   const long long* __restrict__ dropped, phd_flat_layout lay,
@@ -43,6 +46,24 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
     const double np = (double)P.npx;
     const int N = pal_n[img];
 
+    // --- partly accepted tie groups: fold the pixels k_palette_ties accepted into their parent's sums ---
+    {
+        const int nt = tie_n[img];
+        const u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
+        for (int k = tid; k < nt; k += blockDim.x) {
+            const int g = tie_list[(size_t)img * T + k];
+            const GroupPlan gp = plan_g[(size_t)img * T + g];
+            const GroupSums S = phd_reduce_group(ct, P, g, centres[parent_ids[(size_t)img * T + gp.slot]]);
+            SlotAcc* A = sacc + (size_t)img * T + gp.slot;
+            if (S.summax) atomicAdd(&A->summax, S.summax);
+            if (S.n255) atomicAdd(&A->n255, S.n255);
+            if (S.s_sum) atomicAdd(&A->s_sum, S.s_sum);
+            if (S.t_sum) atomicAdd(&A->t_sum, (u64)S.t_sum);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+
     // --- palette averages ---
     const double inv_total = 1.0 / (double)P.hpx;
     for (int j = tid; j < T; j += blockDim.x) {
@@ -50,7 +71,11 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
         int pid = -1;
         if (j < N) {
             pid = parent_ids[(size_t)img * T + j];
-            const SlotAcc A = sacc[(size_t)img * T + j];
+            SlotAcc A;  // read past L1: other threads of this CTA have just added to it with atomics
+            {
+                const u64* q = reinterpret_cast<const u64*>(sacc + (size_t)img * T + j);
+                A.cnt = __ldcg(q); A.summax = __ldcg(q + 1); A.n255 = __ldcg(q + 2); A.s_sum = __ldcg(q + 3); A.t_sum = __ldcg(q + 4);
+            }
             const double off = 180.0 - centres[pid];
             const double inv = 1.0 / (double)A.cnt;
             h = (double)A.t_sum * (1.0 / (double)(1 << PHD_T_SHIFT)) * inv - off;
@@ -171,7 +196,8 @@ void phd_launch_finalize(const DevParams& P, int nimg, const double* centres, co
         cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    k_finalize<<<nimg, 256, smem, st>>>(P, centres, bincount, ws.iacc, ws.pal_n, ws.parent_ids, ws.sacc, ws.binsum,
+    k_finalize<<<nimg, 256, smem, st>>>(P, centres, bincount, ws.iacc, ws.pal_n, ws.parent_ids, ws.sacc, ws.plan,
+                                        ws.tie_list, ws.tie_n, ws.cells_tie, ws.binsum,
                                         ws.maxpow, ws.sharp, ws.boxes, ws.tie_groups, ws.dropped, lay, records_dev);
     *launches += 1;
 }

@@ -1,17 +1,21 @@
-// Pixel front end and palette accumulation.
+// Pixel front end: ONE pass over the packed RGB bytes produces everything the palette, the saturation mean and
+// the channel statistics need.
 //
-//   k_frontend            replaces downsample_rgb / rgb2hsv / get_rgb_statistics / get_hsv_average and the
-//                         counting half of arm_octree (src/image_processing.c:344-417,533-553,
-//                         src/color_quantization.c:108-161): one read of the packed RGB bytes gives the
-//                         channel sums, the saturation sum and the per-chunk palette histogram.
-//   k_palette_accumulate  replaces the pixel moving of group_irregular_pixels and calculate_avg_hsv
-//                         (src/color_quantization.c:342-479,510-576): second pass (RGB is L2 resident)
-//                         that sums wrapped hue / s / v per parent, honouring the tie-path rule
-//                         "first `room` pixels in raster order + the very last pixel".
-//   k_group_sweep         test hook: group id of all 2^24 colours.
+//   k_pixels          replaces downsample_rgb / rgb2hsv / get_rgb_statistics / get_hsv_average, arm_octree and the
+//                     summing of calculate_avg_hsv (src/image_processing.c:344-417,533-553,
+//                     src/color_quantization.c:108-161,510-576).  Every pixel is classified into a CELL
+//                     (pixel_cells.cuh) and its count / max / saturation / hue contributions are added to that
+//                     cell with shared-memory integer atomics; per-parent sums for whatever parents are selected
+//                     later follow from the cells (palette_select.cu), so no second pass over the image is needed.
+//   k_palette_ties    the one part of group_irregular_pixels (src/color_quantization.c:411-451) that depends on
+//                     raster order: tied groups keep "the first `room` pixels + the last pixel".  Only the few
+//                     chunks that hold those pixels are revisited (work list from palette_select).
+//   k_rgb_stats       channel sums over the FULL image when the HSV image is downsampled (src/interface.c:50-55).
+//   k_build_cell_tables / k_build_exc   per-parameter tables, computed with the reference's double arithmetic.
+//   k_group_sweep     test hook: group id of all 2^24 colours.
 //
 // All accumulators are integers (fixed point where needed) so results do not depend on scheduling.
-#include "hsv_fast.cuh"
+#include "pixel_cells.cuh"
 
 namespace {
 
@@ -20,87 +24,191 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ u32 warp_sum_u32(u32 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Pixel i (0..15) of 48 packed bytes as R | G << 8 | B << 16: one byte permute of the two words it straddles.
+__device__ __forceinline__ u32 pixel_word(const u32 (&w)[12], int i) {
+    const int byte = 3 * i, k = byte >> 2, s = byte & 3;
+    if (s == 0) return w[k] & 0x00ffffffu;
+    if (s == 1) return w[k] >> 8;
+    return __byte_perm(w[k], w[k + 1], s == 2 ? 0x7432 : 0x7543);
+}
+
+// Channel sums of 16 pixels: bytes are regrouped into channel-pure words (two permutes each) and reduced with
+// dp4a (sum: dot with 1,1,1,1; sum of squares: dot with itself).
+__device__ __forceinline__ void channel_sums(const u32 (&w)[12], u32 (&sum)[3], u32 (&sq)[3]) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {  // pixels 4g .. 4g+3 live in words 3g .. 3g+2
+        const u32 a = w[3 * g], b = w[3 * g + 1], c = w[3 * g + 2];
+        // bytes of (a,b,c): R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        const u32 r = __byte_perm(__byte_perm(a, b, 0x0630), c, 0x5210);   // R0 R1 R2 R3
+        const u32 gg = __byte_perm(__byte_perm(a, b, 0x0741), c, 0x6210);  // G0 G1 G2 G3
+        const u32 bb = __byte_perm(__byte_perm(a, b, 0x0052), c, 0x7410);  // B0 B1 B2 B3
+        sum[0] = __dp4a(r, 0x01010101u, sum[0]);
+        sum[1] = __dp4a(gg, 0x01010101u, sum[1]);
+        sum[2] = __dp4a(bb, 0x01010101u, sum[2]);
+        sq[0] = __dp4a(r, r, sq[0]);
+        sq[1] = __dp4a(gg, gg, sq[1]);
+        sq[2] = __dp4a(bb, bb, sq[2]);
+    }
+}
+
+// Per-thread run of consecutive pixels that fall into the same cell; flushed with four native 32-bit
+// shared-memory atomics (ATOMS.ADD) when the cell changes.
+struct CellRun {
+    int cell;
+    u32 w0, mx, s, h;
+};
+
+__device__ __forceinline__ void run_flush(uint4* chunkW, CellRun& r) {
+    if (r.cell >= 0) {
+        const u32 n = r.w0 & 0xffffu;
+        u32* c = reinterpret_cast<u32*>(chunkW + r.cell);
+        atomicAdd(c, r.w0);
+        atomicAdd(c + 1, r.mx);
+        atomicAdd(c + 2, r.s - n * PHD_MAGIC_RN_BITS);
+        atomicAdd(c + 3, r.h - n * PHD_MAGIC_RN_BITS);
+    }
+}
+
+__device__ __forceinline__ void run_add(uint4* chunkW, CellRun& r, const PixOut& o) {
+    if (o.cell != r.cell) {
+        run_flush(chunkW, r);
+        r.cell = o.cell; r.w0 = 0; r.mx = 0; r.s = 0; r.h = 0;
+    }
+    r.w0 += o.w0; r.mx += o.mx; r.s += o.sbits; r.h += o.hbits;
+}
 
 // ------------------------------------------------------------------------------------------
-// One CTA per chunk of PHD_CHUNK HSV pixels; each thread owns 16 consecutive pixels (48 bytes, three 16-byte
-// loads).  Histogram increments are run-length merged per thread before they hit shared memory.
-template <bool FUSED_STATS>
-__global__ void __launch_bounds__(PHD_FE_THREADS) k_frontend(const uint8_t* __restrict__ rgb, DevParams P,
-                                                             const unsigned char* __restrict__ pal_tables,
-                                                             u16* __restrict__ counts_chunk, u32* __restrict__ hist,
-                                                             ImageAcc* __restrict__ iacc) {
+// One CTA walks `cpp` consecutive chunks of one image.  A chunk is THREADS*16 HSV pixels; each thread owns 16
+// consecutive pixels (48 bytes, three 16-byte loads).  Shared memory: the parameter tables, the chunk's cell
+// words (4 x u32 per cell, fed by atomics), and the CTA's running cell sums (plain adds in the drain, one owner
+// thread per cell), flushed to the image's global cells once per CTA.
+//   chunk word 0: count | n255 << 16     1: sum max     2: sum s * 2^QS     3: sum hue fraction * 2^QS
+// QS = 32 - log2(chunk pixels), so a whole chunk cannot overflow 32 bits.
+template <int THREADS, bool DS>
+__global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ rgb, DevParams P,
+                                                    const unsigned char* __restrict__ tabs_g,
+                                                    const unsigned char* __restrict__ exc, int cpp,
+                                                    u16* __restrict__ counts_chunk, u64* __restrict__ cells_g,
+                                                    ImageAcc* __restrict__ iacc) {
+    constexpr int CHUNK = THREADS * 16;
+    constexpr int QS = (THREADS == 256) ? 20 : 19;
+    static_assert(THREADS == 256 || THREADS == 512, "chunk size / QS pairs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* k255 = reinterpret_cast<double*>(smem_raw);
-    unsigned char* tb_raw = smem_raw + 256 * sizeof(double);
-    u32* sh_hist = reinterpret_cast<u32*>(tb_raw + phd_pal_tables_bytes(P.sp));
-    __shared__ u64 red[7][PHD_FE_THREADS / 32];
+    const int NC = P.NC;
+    unsigned char* tb_raw = smem_raw;
+    uint4* chunkW = reinterpret_cast<uint4*>(smem_raw + phd_cell_tables_bytes());  // [NC]
+    u64* acc_s = reinterpret_cast<u64*>(chunkW + NC);                              // [NC]
+    u64* acc_h = acc_s + NC;                                                       // [NC]
+    u32* acc_cnt = reinterpret_cast<u32*>(acc_h + NC);                             // [NC]
+    u32* acc_n255 = acc_cnt + NC;
+    u32* acc_mx = acc_n255 + NC;
+    __shared__ u64 red[6][THREADS / 32];
 
-    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
-    phd_fill_k255(k255);
-    phd_pal_tables_to_smem(tb_raw, pal_tables, P.sp);
-    for (int g = tid; g < P.T; g += blockDim.x) sh_hist[g] = 0;
+    phd_cell_tabs_to_smem(tb_raw, tabs_g);
+    for (int i = tid; i < NC; i += THREADS) {
+        chunkW[i] = make_uint4(0, 0, 0, 0);
+        acc_s[i] = 0; acc_h[i] = 0; acc_cnt[i] = 0; acc_n255[i] = 0; acc_mx[i] = 0;
+    }
     __syncthreads();
-    const PalTablesView tb = phd_pal_tables_view(tb_raw);
-    const FastCfg C = phd_fast_cfg(P);
+    const CellTabs tb = phd_cell_tabs(tb_raw);
+    const CellCfg K = phd_cell_cfg(P, QS);
+    const int spvp = P.sp * P.vp, hp = P.hp, npairs_colour = spvp * hp;
 
-    const long long p0 = (long long)chunk * PHD_CHUNK + (long long)tid * PHD_PX_PER_THREAD;
-    u64 s_acc = 0;
     u32 sum[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
-    int run_gid = -1;
-    u32 run_n = 0;
-    if (p0 < P.hpx) {
-        u32 w[12];
-        if (P.ds <= 1) phd_load48(base + p0 * 3, w, P.aligned16 != 0, (P.hpx - p0) * 3);
+    const int c_begin = blockIdx.x * cpp, c_end = min(c_begin + cpp, P.nchunks);
+    for (int chunk = c_begin; chunk < c_end; chunk++) {
+        const long long p0 = (long long)chunk * CHUNK + (long long)tid * 16;
+        if (p0 < P.hpx) {
+            CellRun run{-1, 0, 0, 0, 0};
+            if (!DS) {
+                u32 w[12];
+                phd_load48(base + p0 * 3, w, P.aligned16 != 0, (P.hpx - p0) * 3);
+                channel_sums(w, sum, sq);  // bytes past the image end were loaded as zeros
+                if (p0 + 16 <= P.hpx) {
 #pragma unroll
-        for (int i = 0; i < PHD_PX_PER_THREAD; i++) {
-            if (p0 + i < P.hpx) {
-                int R, G, B;
-                if (P.ds <= 1) {
-                    R = phd_byte_of(w, 3 * i); G = phd_byte_of(w, 3 * i + 1); B = phd_byte_of(w, 3 * i + 2);
+                    for (int i = 0; i < 16; i++) run_add(chunkW, run, phd_pixel(pixel_word(w, i), tb, K, exc));
                 } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (p0 + i < P.hpx) run_add(chunkW, run, phd_pixel(pixel_word(w, i), tb, K, exc));
+                }
+            } else {
+                for (int i = 0; i < 16 && p0 + i < P.hpx; i++) {
                     const uint8_t* q = base + phd_src_index(p0 + i, P) * 3;
-                    R = __ldg(q); G = __ldg(q + 1); B = __ldg(q + 2);
-                }
-                const FastPx px = phd_group_fast(R, G, B, tb, C, k255);
-                if (px.gid != run_gid) {
-                    if (run_n) atomicAdd(&sh_hist[run_gid], run_n);
-                    run_gid = px.gid;
-                    run_n = 0;
-                }
-                run_n++;
-                s_acc += phd_sat_q30(px, tb);
-                if (FUSED_STATS) {
-                    sum[0] += R; sum[1] += G; sum[2] += B;
-                    sq[0] += R * R; sq[1] += G * G; sq[2] += B * B;
+                    const u32 c = (u32)__ldg(q) | ((u32)__ldg(q + 1) << 8) | ((u32)__ldg(q + 2) << 16);
+                    run_add(chunkW, run, phd_pixel(c, tb, K, exc));
                 }
             }
+            run_flush(chunkW, run);
         }
-        if (run_n) atomicAdd(&sh_hist[run_gid], run_n);
-    }
-    // block reduction of the scalar sums -> one 64-bit global atomic each
-    u64 vals[7] = {s_acc, sum[0], sum[1], sum[2], sq[0], sq[1], sq[2]};
-    const int lane = tid & 31, wid = tid >> 5;
+        __syncthreads();
+        // drain: chunk words -> running sums, per-chunk group counts (needed for raster ranks in the tie path)
+        u16* cc = counts_chunk + ((size_t)img * P.nchunks + chunk) * P.T;
+        auto drain_pair = [&](int pair) -> u32 {
+            u32 cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 7; k++) {
-        if (!FUSED_STATS && k > 0) break;
-        u64 v = warp_sum_u64(vals[k]);
-        if (lane == 0) red[k][wid] = v;
+            for (int sub = 0; sub < 4; sub++) {
+                const int cell = pair * 4 + sub;
+                const uint4 v = chunkW[cell];
+                if (v.x) {
+                    cnt += v.x & 0xffffu;
+                    acc_cnt[cell] += v.x & 0xffffu;
+                    acc_n255[cell] += v.x >> 16;
+                    acc_mx[cell] += v.y;
+                    acc_s[cell] += v.z;
+                    acc_h[cell] += v.w;
+                    chunkW[cell] = make_uint4(0, 0, 0, 0);
+                }
+            }
+            return cnt;
+        };
+        for (int pair = tid; pair < npairs_colour; pair += THREADS) {
+            const int cls = pair / hp, j = pair - cls * hp;
+            cc[j * spvp + cls] = (u16)drain_pair(pair);
+        }
+        if (wid < 2) {  // gray (warp 0) and black (warp 1): all hue bins collapse into one group
+            u32 cnt = 0;
+            for (int j = lane; j < hp; j += 32) cnt += drain_pair((spvp + wid) * hp + j);
+            cnt = warp_sum_u32(cnt);
+            if (lane == 0) cc[wid == 0 ? P.T - (P.vp + 1) : P.T - 1] = (u16)cnt;
+        }
+        if (tid >= 64 && tid < 64 + P.vp - 1) cc[P.T - P.vp + (tid - 64)] = 0;  // gray groups 2.. are never used
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid < 7 && (FUSED_STATS || tid == 0)) {
-        u64 v = 0;
-        for (int w = 0; w < PHD_FE_THREADS / 32; w++) v += red[tid][w];
-        ImageAcc* a = iacc + img;
-        u64* dst = tid == 0 ? &a->s_sum : (tid <= 3 ? &a->sum[tid - 1] : &a->sumsq[tid - 4]);
-        if (v) atomicAdd(dst, v);
+
+    // flush the CTA's cell sums (Q20 in global memory whatever QS is) and the channel sums
+    u64* cg = cells_g + (size_t)img * PHD_CELL_Q * NC;
+    for (int i = tid; i < NC; i += THREADS) {
+        const u32 n = acc_cnt[i];
+        if (n) {
+            atomicAdd(cg + i, (u64)n);
+            if (acc_n255[i]) atomicAdd(cg + NC + i, (u64)acc_n255[i]);
+            atomicAdd(cg + 2 * NC + i, (u64)acc_mx[i]);
+            atomicAdd(cg + 3 * NC + i, acc_s[i] << (20 - QS));
+            atomicAdd(cg + 4 * NC + i, acc_h[i] << (20 - QS));
+        }
     }
-    // per-chunk histogram (needed for raster ranks in the tie path) + image histogram
-    u16* cc = counts_chunk + ((size_t)img * P.nchunks + chunk) * P.T;
-    for (int g = tid; g < P.T; g += blockDim.x) {
-        const u32 c = sh_hist[g];
-        cc[g] = (u16)c;
-        if (c) atomicAdd(&hist[(size_t)img * P.T + g], c);
+    if (!DS) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const u64 a = warp_sum_u64(sum[k]), b = warp_sum_u64(sq[k]);
+            if (lane == 0) { red[k][wid] = a; red[3 + k][wid] = b; }
+        }
+        __syncthreads();
+        if (tid < 6) {
+            u64 v = 0;
+            for (int w = 0; w < THREADS / 32; w++) v += red[tid][w];
+            ImageAcc* a = iacc + img;
+            if (v) atomicAdd(tid < 3 ? &a->sum[tid] : &a->sumsq[tid - 3], v);
+        }
     }
 }
 
@@ -132,283 +240,276 @@ __global__ void __launch_bounds__(256) k_rgb_stats(const uint8_t* __restrict__ r
 }
 
 // ------------------------------------------------------------------------------------------
-// Per-thread run of consecutive pixels that go to the same parent slot; flushed with native 32-bit
-// shared-memory atomics (ATOMS.ADD) when the slot changes.
-struct SlotRun {
-    int slot;
-    u32 summax, n255;
-    u64 s, t;
-};
-
-struct SlotSm {
-    u32* summax; u32* n255; u32* s_lo; u32* s_hi; u32* t_lo; u32* t_hi;
-};
-
-__device__ __forceinline__ void run_flush(const SlotSm& S, SlotRun& r) {
-    if (r.slot >= 0) {
-        atomicAdd(&S.summax[r.slot], r.summax);
-        if (r.n255) atomicAdd(&S.n255[r.slot], r.n255);
-        atomicAdd(&S.s_lo[r.slot], (u32)(r.s & 0xffffull));
-        atomicAdd(&S.s_hi[r.slot], (u32)(r.s >> 16));
-        atomicAdd(&S.t_lo[r.slot], (u32)(r.t & 0xffffull));
-        atomicAdd(&S.t_hi[r.slot], (u32)(r.t >> 16));
-    }
-    r.slot = -1; r.summax = 0; r.n255 = 0; r.s = 0; r.t = 0;
-}
-
-// Adds one pixel to its parent slot: t = wrap(h + off) as calculate_avg_hsv does (color_quantization.c:538-548).
-// The wrap decision is discrete; within 0.01 degree of the 0/360 seam it is taken from the exact FP64 replay.
-__device__ __forceinline__ void run_add(const SlotSm& S, SlotRun& r, int slot, long long off_q, double off_d,
-                                        const FastPx& px, const PalTablesView& tb, int R, int G, int B,
-                                        const double* __restrict__ k255) {
-    if (slot != r.slot) {
-        run_flush(S, r);
-        r.slot = slot;
-    }
-    long long t = phd_hue_q22(px, tb) + off_q;
-    const long long eps = (1ll << PHD_HQ_SHIFT) / 100;
-    const long long d360 = t - PHD_HQ_360;
-    if ((d360 > -eps && d360 < eps) || (t > -eps && t < eps)) {
-        const HsvD e = phd_hsv_exact(R, G, B, k255);
-        const double te = __dadd_rn(e.h, off_d);
-        if (te > 360.0) t -= PHD_HQ_360;
-        else if (te < 0.0) t += PHD_HQ_360;
-        if (t < 0) t = 0;  // the fixed-point value may sit a hair on the other side of the seam
-    } else if (t > PHD_HQ_360) t -= PHD_HQ_360;
-    else if (t < 0) t += PHD_HQ_360;
-    r.t += (u64)t;
-    r.s += phd_sat_q30(px, tb);
-    r.summax += (u32)px.mx;
-    r.n255 += (px.mx == 255);
-}
-
-__global__ void __launch_bounds__(PHD_FE_THREADS) k_palette_accumulate(
-    const uint8_t* __restrict__ rgb, DevParams P, const double* __restrict__ centres,
-    const unsigned char* __restrict__ pal_tables, const GroupPlan* __restrict__ plan_g,
-    const int* __restrict__ pal_n, const int* __restrict__ parent_ids, const int* __restrict__ tie_list,
-    const int* __restrict__ tie_n, SlotAcc* __restrict__ sacc) {
+// Tie path.  Work item = (image, chunk) holding pixels of a tied group that are only PARTLY accepted.  The chunk
+// is classified again; accepted pixels (chunks before the group's c* entirely, the first `need` pixels of chunk
+// c* in raster order, and the group's very last pixel) are added to the image's tie cells, which finalize folds
+// into the parents with the same cell arithmetic as everything else.
+__global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict__ rgb, DevParams P,
+                                                      const unsigned char* __restrict__ tabs_g,
+                                                      const unsigned char* __restrict__ exc,
+                                                      const GroupPlan* __restrict__ plan_g,
+                                                      const int* __restrict__ tie_list, const int* __restrict__ tie_n,
+                                                      const u32* __restrict__ work, const u32* __restrict__ work_n,
+                                                      u64* __restrict__ cells_tie) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = P.T;
-    double* k255 = reinterpret_cast<double*>(smem_raw);
-    unsigned char* tb_raw = smem_raw + 256 * sizeof(double);    // 16-byte aligned, size multiple of 16
-    double* off = reinterpret_cast<double*>(tb_raw + phd_pal_tables_bytes(P.sp));  // [T]
-    long long* off_q = reinterpret_cast<long long*>(off + T);   // [T]
-    GroupPlan* plan = reinterpret_cast<GroupPlan*>(off_q + T);  // [T]
-    u32* acc = reinterpret_cast<u32*>(plan + T);                // [6][T]
-    u16* gid_cache = reinterpret_cast<u16*>(acc + 6 * T);       // [PHD_CHUNK]
-    __shared__ int scan[PHD_FE_THREADS];
+    unsigned char* tb_raw = smem_raw;
+    u16* gid_cache = reinterpret_cast<u16*>(smem_raw + phd_cell_tables_bytes());  // [chunk]
+    __shared__ int scan[256];
     __shared__ int sh_last;
-
-    const int img = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-    const uint8_t* base = rgb + (size_t)img * P.image_stride;
-    const int N = pal_n[img];
-    phd_fill_k255(k255);
-    phd_pal_tables_to_smem(tb_raw, pal_tables, P.sp);
-    for (int g = tid; g < T; g += blockDim.x) plan[g] = plan_g[(size_t)img * T + g];
-    for (int j = tid; j < N; j += blockDim.x) {
-        const double o = __dsub_rn(180.0, centres[parent_ids[(size_t)img * T + j]]);
-        off[j] = o;
-        off_q[j] = __double2ll_rn(o * (double)(1 << PHD_HQ_SHIFT));
-    }
-    for (int i = tid; i < 6 * T; i += blockDim.x) acc[i] = 0;
+    const int tid = threadIdx.x, T = P.T, NC = P.NC;
+    const int ppt = P.chunk / 256;  // consecutive pixels per thread (16 or 32)
+    const u32 n_items = *work_n;
+    if (blockIdx.x >= n_items) return;
+    phd_cell_tabs_to_smem(tb_raw, tabs_g);
     __syncthreads();
-    const PalTablesView tb = phd_pal_tables_view(tb_raw);
-    const FastCfg C = phd_fast_cfg(P);
-    SlotSm S{acc, acc + T, acc + 2 * T, acc + 3 * T, acc + 4 * T, acc + 5 * T};
-    SlotRun run{-1, 0, 0, 0, 0};
+    const CellTabs tb = phd_cell_tabs(tb_raw);
+    // the tables carry 2^QS / max for the front end's QS; tie cells are kept in Q20 like the global cells
+    const int qs = (P.fe_threads == 256) ? 20 : 19;
+    const CellCfg K = phd_cell_cfg(P, qs);
 
-    const long long p0 = (long long)chunk * PHD_CHUNK + (long long)tid * PHD_PX_PER_THREAD;
-    u32 w[12];
-    if (p0 < P.hpx && P.ds <= 1) phd_load48(base + p0 * 3, w, P.aligned16 != 0, (P.hpx - p0) * 3);
-#pragma unroll
-    for (int i = 0; i < PHD_PX_PER_THREAD; i++) {
-        int gid = 0xffff;
-        if (p0 + i < P.hpx) {
-            int R, G, B;
-            if (P.ds <= 1) {
-                R = phd_byte_of(w, 3 * i); G = phd_byte_of(w, 3 * i + 1); B = phd_byte_of(w, 3 * i + 2);
-            } else {
-                const uint8_t* q = base + phd_src_index(p0 + i, P) * 3;
-                R = __ldg(q); G = __ldg(q + 1); B = __ldg(q + 2);
+    auto pixel_at = [&](const uint8_t* base, long long i) -> u32 {
+        const uint8_t* q = base + phd_src_index(i, P) * 3;
+        return (u32)__ldg(q) | ((u32)__ldg(q + 1) << 8) | ((u32)__ldg(q + 2) << 16);
+    };
+    auto accept = [&](u64* ct, const PixOut& o) {
+        atomicAdd(ct + o.cell, 1ull);
+        if (o.w0 >> 16) atomicAdd(ct + NC + o.cell, 1ull);
+        atomicAdd(ct + 2 * NC + o.cell, (u64)o.mx);
+        atomicAdd(ct + 3 * NC + o.cell, (u64)(o.sbits - PHD_MAGIC_RN_BITS) << (20 - qs));
+        atomicAdd(ct + 4 * NC + o.cell, (u64)(o.hbits - PHD_MAGIC_RN_BITS) << (20 - qs));
+    };
+
+    for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int img = (int)(work[item] / (u32)P.nchunks), chunk = (int)(work[item] % (u32)P.nchunks);
+        const uint8_t* base = rgb + (size_t)img * P.image_stride;
+        const GroupPlan* plan = plan_g + (size_t)img * T;
+        u64* ct = cells_tie + (size_t)img * PHD_CELL_Q * NC;
+        const long long c0 = (long long)chunk * P.chunk;
+        __syncthreads();  // gid_cache of the previous item is no longer read
+        for (int i = 0; i < ppt; i++) {
+            const int li = tid * ppt + i;
+            int gid = 0xffff;
+            if (c0 + li < P.hpx) {
+                const PixOut o = phd_pixel(pixel_at(base, c0 + li), tb, K, exc);
+                gid = phd_cell_group(o.cell, P);
+                const GroupPlan gp = plan[gid];
+                if (gp.mode == 2 && chunk < gp.cstar) accept(ct, o);  // whole chunk accepted
             }
-            const FastPx px = phd_group_fast(R, G, B, tb, C, k255);
-            gid = px.gid;
-            const GroupPlan gp = plan[gid];
-            if (gp.mode == 1 || (gp.mode == 2 && chunk < gp.cstar))
-                run_add(S, run, gp.slot, off_q[gp.slot], off[gp.slot], px, tb, R, G, B, k255);
+            gid_cache[li] = (u16)gid;
         }
-        gid_cache[tid * PHD_PX_PER_THREAD + i] = (u16)gid;
-    }
-    run_flush(S, run);
-    __syncthreads();
-
-    // Tie groups whose partial chunk, or whose last pixel, falls in this chunk: ordered pass.
-    const int nt = tie_n[img];
-    for (int k = 0; k < nt; k++) {
-        const int g = tie_list[(size_t)img * T + k];
-        const GroupPlan gp = plan[g];
-        const bool partial = (gp.cstar == chunk && gp.need > 0);
-        const bool last = (gp.clast == chunk);
-        if (!partial && !last) continue;  // uniform across the block
-        int mine = 0, my_last = -1;
-#pragma unroll
-        for (int i = 0; i < PHD_PX_PER_THREAD; i++)
-            if (gid_cache[tid * PHD_PX_PER_THREAD + i] == g) { mine++; my_last = tid * PHD_PX_PER_THREAD + i; }
-        scan[tid] = mine;
-        if (tid == 0) sh_last = -1;
         __syncthreads();
-        if (tid == 0) {
-            int acc_run = 0;
-            for (int t = 0; t < PHD_FE_THREADS; t++) { int c = scan[t]; scan[t] = acc_run; acc_run += c; }
+        const int nt = tie_n[img];
+        for (int k = 0; k < nt; k++) {
+            const int g = tie_list[(size_t)img * T + k];
+            const GroupPlan gp = plan[g];
+            const bool partial = (gp.mode == 2 && gp.cstar == chunk && gp.need > 0);
+            const bool last = (gp.mode == 2 && gp.clast == chunk);
+            if (!partial && !last) continue;  // uniform across the block
+            int mine = 0, my_last = -1;
+            for (int i = 0; i < ppt; i++)
+                if (gid_cache[tid * ppt + i] == g) { mine++; my_last = tid * ppt + i; }
+            scan[tid] = mine;
+            if (tid == 0) sh_last = -1;
+            __syncthreads();
+            if (tid == 0) {
+                int run = 0;
+                for (int t = 0; t < 256; t++) { const int c = scan[t]; scan[t] = run; run += c; }
+            }
+            if (my_last >= 0) atomicMax(&sh_last, my_last);
+            __syncthreads();
+            int rank = scan[tid];
+            const int last_idx = sh_last;
+            for (int i = 0; i < ppt; i++) {
+                const int li = tid * ppt + i;
+                if (gid_cache[li] != g) continue;
+                const bool take = (partial && rank < gp.need) || (last && li == last_idx);
+                rank++;
+                if (take) accept(ct, phd_pixel(pixel_at(base, c0 + li), tb, K, exc));
+            }
+            __syncthreads();
         }
-        if (my_last >= 0) atomicMax(&sh_last, my_last);
-        __syncthreads();
-        int rank = scan[tid];
-        const int last_idx = sh_last;
-        for (int i = 0; i < PHD_PX_PER_THREAD; i++) {
-            const int li = tid * PHD_PX_PER_THREAD + i;
-            if (gid_cache[li] != g) continue;
-            const bool take = (partial && rank < gp.need) || (last && li == last_idx);
-            rank++;
-            if (!take) continue;
-            const uint8_t* q = base + phd_src_index((long long)chunk * PHD_CHUNK + li, P) * 3;
-            const int R = __ldg(q), G = __ldg(q + 1), B = __ldg(q + 2);
-            const FastPx px = phd_group_fast(R, G, B, tb, C, k255);
-            run_add(S, run, gp.slot, off_q[gp.slot], off[gp.slot], px, tb, R, G, B, k255);
-        }
-        run_flush(S, run);
-        __syncthreads();
-    }
-    __syncthreads();
-
-    for (int j = tid; j < N; j += blockDim.x) {
-        const u64 sm = S.summax[j];
-        const u64 sv = ((u64)S.s_hi[j] << 16) + S.s_lo[j];
-        const u64 tv = ((u64)S.t_hi[j] << 16) + S.t_lo[j];
-        if (!(sm | sv | tv)) continue;
-        SlotAcc* a = sacc + (size_t)img * T + j;
-        atomicAdd(&a->summax, sm);
-        if (S.n255[j]) atomicAdd(&a->n255, (u64)S.n255[j]);
-        if (sv) atomicAdd(&a->s_sum, sv);
-        if (tv) atomicAdd(&a->t_sum, tv);
     }
 }
 
+// ------------------------------------------------------------------------------------------
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_group_sweep(DevParams P, const unsigned char* __restrict__ pal_tables,
-                                                     u16* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_group_sweep(DevParams P, const unsigned char* __restrict__ tabs_g,
+                                                     const unsigned char* __restrict__ exc, u16* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* k255 = reinterpret_cast<double*>(smem_raw);
     unsigned char* tb_raw = smem_raw + 256 * sizeof(double);
     phd_fill_k255(k255);
-    if (FAST) phd_pal_tables_to_smem(tb_raw, pal_tables, P.sp);
+    if (FAST) phd_cell_tabs_to_smem(tb_raw, tabs_g);
     __syncthreads();
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;  // r<<16 | g<<8 | b
     const int R = (c >> 16) & 255, G = (c >> 8) & 255, B = c & 255;
     if (FAST) {
-        const PalTablesView tb = phd_pal_tables_view(tb_raw);
-        const FastCfg C = phd_fast_cfg(P);
-        out[c] = (u16)phd_group_fast(R, G, B, tb, C, k255).gid;
+        const CellTabs tb = phd_cell_tabs(tb_raw);
+        const CellCfg K = phd_cell_cfg(P, 20);
+        const PixOut o = phd_pixel((u32)R | ((u32)G << 8) | ((u32)B << 16), tb, K, exc);
+        out[c] = (u16)phd_cell_group(o.cell, P);
     } else {
         const HsvD px = phd_hsv_exact(R, G, B, k255);
         out[c] = (u16)phd_group_exact(px, P);
     }
 }
 
-// Builds the per-parameter tables with the exact arithmetic; one thread per max value.
-__global__ void __launch_bounds__(256) k_build_pal_tables(DevParams P, unsigned char* __restrict__ out,
-                                                          int* __restrict__ ok) {
+// Per-parameter tables with the reference's arithmetic (pixel_cells.cuh); one thread per max value.
+__global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, int qs, unsigned char* __restrict__ out,
+                                                           int* __restrict__ ok) {
     __shared__ double k255[256];
     phd_fill_k255(k255);
     __syncthreads();
     const int m = threadIdx.x;
-    unsigned char* vtab = out;
-    u64* rs = reinterpret_cast<u64*>(out + 256);
-    u64* rh = reinterpret_cast<u64*>(out + 256 + 2048);
-    u32* rd = reinterpret_cast<u32*>(out + 256 + 4096);
-    u16* sthr = reinterpret_cast<u16*>(out + 256 + 4096 + 1024);
-    const int spw = phd_spw(P.sp);
+    unsigned char* svtab = out;
+    float2* qtab = reinterpret_cast<float2*>(out + PHD_TRI_SIZE);
+    uint2* mtab = reinterpret_cast<uint2*>(out + PHD_TRI_SIZE + 2048);
+    const int spvp = P.sp * P.vp;
     // value bin / black (rgb2hsv :408, arm_octree :129,141)
     const double v = (m == 255) ? 0.999999 : k255[m];
-    int vi = 0xFF;
-    if (!(v < P.bt)) vi = min(max((int)__ddiv_rn(__dsub_rn(v, P.bt), P.Lv), 0), 254);
-    vtab[m] = (unsigned char)vi;
-    rs[m] = m ? ((1ull << 46) + (u64)(m / 2)) / (u64)m : 0ull;
-    rh[m] = m ? ((60ull << 38) + (u64)(m / 2)) / (u64)m : 0ull;
-    {
-        const u64 den = (u64)(int)P.Lh * (u64)m;
-        rd[m] = den ? (u32)(((1ull << 32) + den - 1) / den) : 0u;
-    }
-    // saturation classes along min = 0..m: gray (-1) or Si, must be non-increasing
-    u16* th = sthr + m * spw;
-    for (int j = 0; j < spw; j++) th[j] = j < P.sp ? 0xFFFF : 0;
-    int prev = 1 << 30;
-    bool mono = true;
+    const bool black = v < P.bt;
+    const int vi_raw = black ? 0 : (int)__ddiv_rn(__dsub_rn(v, P.bt), P.Lv);
+    if (vi_raw < 0 || vi_raw >= P.vp) atomicAnd(ok, 0);  // the reference would index past its grid
+    const int vi = min(max(vi_raw, 0), P.vp - 1);
     for (int mn = 0; mn <= m; mn++) {
         double s;
         if (m == 0) s = 0.0;
         else if (mn == 0) s = 0.999999;
         else s = __ddiv_rn(__dsub_rn(k255[m], k255[mn]), k255[m]);
-        int c = -1;
-        if (!(s < P.gt)) c = (int)__ddiv_rn(__dsub_rn(s, P.gt), P.Ls);
-        if (c > prev || c >= P.sp) mono = false;
-        // first min at which the class drops below j
-        for (int j = 0; j < P.sp; j++)
-            if (c < j && th[j] == 0xFFFF) th[j] = (u16)mn;
-        prev = c;
+        int cls;
+        if (black) cls = spvp + 1;
+        else if (s < P.gt) cls = spvp;
+        else {
+            const int si = (int)__ddiv_rn(__dsub_rn(s, P.gt), P.Ls);
+            if (si < 0 || si >= P.sp) atomicAnd(ok, 0);
+            cls = min(max(si, 0), P.sp - 1) * P.vp + vi;
+        }
+        svtab[((m * m + m) >> 1) + mn] = (unsigned char)cls;
     }
-    if (!mono) atomicAnd(ok, 0);
+    const int Lhi = (int)P.Lh;
+    qtab[m] = m ? make_float2((float)(1.0 / (double)(Lhi * m)), (float)(Lhi * m)) : make_float2(0.f, 0.f);
+    mtab[m] = make_uint2(m ? __float_as_uint((float)((double)(1u << qs) / (double)m)) : 0u,
+                         1u + ((m == 255) ? 65536u : 0u));
+}
+
+// Exceptional-colour codes (pixel_cells.cuh): for every colour whose hue is exactly k * Lh/2, what the reference's
+// doubles make of it.  code = (cell delta << 1) | full, relative to the ordinary cell cls*4hp + 2k + 1.
+__global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* __restrict__ out, int* __restrict__ ok) {
+    __shared__ double k255[256];
+    phd_fill_k255(k255);
+    __syncthreads();
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;  // R | G << 8 | B << 16
+    const int R = c & 255, G = (c >> 8) & 255, B = (c >> 16) & 255;
+    const int mx = max(R, max(G, B)), mn = min(R, min(G, B)), q = mx - mn;
+    int code = 0;
+    if (q != 0) {
+        const bool isR = (R == mx), isG = (G == mx);
+        const int p = isR ? (G - B) : (isG ? (B - R) : (R - G));
+        int num2 = 120 * ((isR ? 0 : (isG ? 2 : 4)) * q + p);
+        if (num2 < 0) num2 += 720 * q;
+        const int Lhi = (int)P.Lh, den = Lhi * q;
+        if (num2 % den == 0) {
+            const int k = num2 / den;                   // the pixel sits exactly on b = k * Lh/2
+            const double b = (double)k * (P.Lh * 0.5);  // exact (Lh is a small integer)
+            const HsvD e = phd_hsv_exact(R, G, B, k255);
+            const int hi_ref = (int)__ddiv_rn(e.h, P.Lh);
+            // side of a wrap seam at b (calculate_avg_hsv :538-548): t = h + off with b + off == 0 or 360
+            bool below;
+            if (b < 180.0) below = __dadd_rn(e.h, -b) < 0.0;               // t < 0 -> t + 360 (ends near 360)
+            else below = !(__dadd_rn(e.h, __dsub_rn(360.0, b)) > 360.0);   // not wrapped (stays near 360)
+            int delta, full = 0;
+            if ((k & 1) == 0) {
+                const int dj = hi_ref - (k >> 1);
+                if (dj == 0) delta = below ? -1 : 0;  // (j, on the lower edge, low side) | (j, lower half)
+                else if (dj == -1 && k > 0) {         // (j-1, end of the upper half) | (j-1, on the upper edge)
+                    delta = below ? -2 : -3;
+                    full = below ? 1 : 0;
+                } else {
+                    delta = 0;
+                    atomicAnd(ok, 0);
+                }
+            } else {
+                if (hi_ref != (k >> 1)) atomicAnd(ok, 0);
+                delta = below ? -2 : 0;  // (j, end of the lower half) | (j, upper half)
+                full = below ? 1 : 0;
+            }
+            code = delta * 2 + full;
+        }
+    }
+    out[c] = (unsigned char)(signed char)code;
 }
 
 }  // namespace
 
-void phd_launch_frontend(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* pal_tables,
-                         Workspace& ws, cudaStream_t st, int* launches) {
-    dim3 grid(P.nchunks, nimg);
-    const size_t smem = 256 * sizeof(double) + phd_pal_tables_bytes(P.sp) + (size_t)P.T * sizeof(u32);
+// ------------------------------------------------------------------------------------------
+size_t phd_pixels_smem(const DevParams& P) {
+    return phd_cell_tables_bytes() + (size_t)P.NC * (sizeof(uint4) + 2 * sizeof(u64) + 3 * sizeof(u32));
+}
+
+void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                       const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
+    const size_t smem = phd_pixels_smem(P);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_frontend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_frontend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    if (P.ds <= 1) {
-        k_frontend<true><<<grid, PHD_FE_THREADS, smem, st>>>(rgb, P, pal_tables, ws.counts_chunk, ws.hist, ws.iacc);
-        *launches += 1;
+    // chunks per CTA: long walks amortise the table load and the final flush; enough CTAs to fill 148 SMs
+    long long total = (long long)P.nchunks * nimg;
+    int cpp = (int)(total / (148 * 12));
+    cpp = cpp < 1 ? 1 : (cpp > 32 ? 32 : cpp);
+    dim3 grid((P.nchunks + cpp - 1) / cpp, nimg);
+    const bool ds = P.ds > 1;
+    if (P.fe_threads == 256) {
+        if (ds) k_pixels<256, true><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+        else k_pixels<256, false><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
     } else {
-        k_frontend<false><<<grid, PHD_FE_THREADS, smem, st>>>(rgb, P, pal_tables, ws.counts_chunk, ws.hist, ws.iacc);
+        if (ds) k_pixels<512, true><<<grid, 512, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+        else k_pixels<512, false><<<grid, 512, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+    }
+    *launches += 1;
+    if (ds) {
         int blocks = (int)((P.npx + 256LL * 16 - 1) / (256LL * 16));
         if (blocks < 1) blocks = 1;
         k_rgb_stats<<<dim3(blocks, nimg), 256, 0, st>>>(rgb, P, ws.iacc);
-        *launches += 2;
+        *launches += 1;
     }
 }
 
-void phd_launch_palette_accumulate(const uint8_t* rgb, const DevParams& P, int nimg, const double* centres,
-                                   const unsigned char* pal_tables, Workspace& ws, cudaStream_t st, int* launches) {
-    dim3 grid(P.nchunks, nimg);
-    const size_t smem = 256 * sizeof(double) +
-                        (size_t)P.T * (sizeof(double) + sizeof(long long) + sizeof(GroupPlan) + 6 * sizeof(u32)) +
-                        PHD_CHUNK * sizeof(u16) + phd_pal_tables_bytes(P.sp);
+void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                             const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
+    const size_t smem = phd_cell_tables_bytes() + (size_t)P.chunk * sizeof(u16);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_palette_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_palette_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    k_palette_accumulate<<<grid, PHD_FE_THREADS, smem, st>>>(rgb, P, centres, pal_tables, ws.plan, ws.pal_n,
-                                                             ws.parent_ids, ws.tie_list, ws.tie_n, ws.sacc);
+    int grid = nimg * 4;
+    if (grid > 148 * 4) grid = 148 * 4;
+    k_palette_ties<<<grid, 256, smem, st>>>(rgb, P, tabs, exc, ws.plan, ws.tie_list, ws.tie_n, ws.work, ws.work_n,
+                                            ws.cells_tie);
     *launches += 1;
 }
 
-void phd_launch_group_sweep(const DevParams& P, const unsigned char* pal_tables, bool fast, u16* out_dev,
-                            cudaStream_t st) {
-    const size_t smem = 256 * sizeof(double) + phd_pal_tables_bytes(P.sp);
-    if (fast) k_group_sweep<true><<<(1 << 24) / 256, 256, smem, st>>>(P, pal_tables, out_dev);
-    else k_group_sweep<false><<<(1 << 24) / 256, 256, smem, st>>>(P, pal_tables, out_dev);
+void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const unsigned char* exc, bool fast,
+                            u16* out_dev, cudaStream_t st) {
+    const size_t smem = 256 * sizeof(double) + phd_cell_tables_bytes();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_group_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set = true;
+    }
+    if (fast) k_group_sweep<true><<<(1 << 24) / 256, 256, smem, st>>>(P, tabs, exc, out_dev);
+    else k_group_sweep<false><<<(1 << 24) / 256, 256, 256 * sizeof(double), st>>>(P, tabs, exc, out_dev);
 }
 
-void phd_launch_build_pal_tables(const DevParams& P, unsigned char* tables_dev, int* ok_dev, cudaStream_t st) {
-    k_build_pal_tables<<<1, 256, 0, st>>>(P, tables_dev, ok_dev);
+void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev, unsigned char* exc_dev, int* ok_dev,
+                                  cudaStream_t st) {
+    k_build_cell_tables<<<1, 256, 0, st>>>(P, P.fe_threads == 256 ? 20 : 19, tables_dev, ok_dev);
+    k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
 }
 
-size_t phd_pal_tables_size(int sp) { return phd_pal_tables_bytes(sp); }
+size_t phd_cell_tables_size() { return phd_cell_tables_bytes(); }

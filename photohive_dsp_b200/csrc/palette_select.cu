@@ -11,7 +11,7 @@
 // :303-311) and pixels beyond the tail node's free room are dropped except the last (:435-440).
 #include <limits.h>
 
-#include "phd_internal.h"
+#include "cell_reduce.cuh"
 
 namespace {
 
@@ -39,12 +39,15 @@ __device__ double centre_dist(const double* gh, const double* gs, const double* 
 
 __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const double* __restrict__ centres,
                                                         const float* __restrict__ sv_f,
-                                                        const u32* __restrict__ hist,
+                                                        const u64* __restrict__ cells_g,
                                                         const u16* __restrict__ counts_chunk,
                                                         GroupPlan* __restrict__ plan_g, int* __restrict__ pal_n,
                                                         int* __restrict__ parent_ids, int* __restrict__ tie_list,
                                                         int* __restrict__ tie_n, int* __restrict__ tie_groups,
-                                                        long long* __restrict__ dropped, SlotAcc* __restrict__ sacc) {
+                                                        long long* __restrict__ dropped, SlotAcc* __restrict__ sacc,
+                                                        u32* __restrict__ hist, ImageAcc* __restrict__ iacc,
+                                                        u64* __restrict__ cells_tie_g, u32* __restrict__ work,
+                                                        u32* __restrict__ work_n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = P.T, tid = threadIdx.x, img = blockIdx.x;
     int* n = reinterpret_cast<int*>(smem_raw);       // [T] pixel counts
@@ -58,16 +61,46 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     int* take = pend + T;                            // [T] tie groups: pixels accepted from the front
     int* keep = take + T;                            // [T] tie groups: last pixel survives
     int* scnt = keep + T;                            // [T] per parent slot: pixels that end up in it
+    u32* cbits = reinterpret_cast<u32*>(scnt + T);   // [(nchunks+31)/32] chunks the tie path must revisit
     __shared__ int sh_N, sh_nt;
+    __shared__ u64 sh_ssum;
 
     const double* gh = centres;
     const double* gs = centres + T;
     const double* gv = centres + 2 * T;
-    const u32* h = hist + (size_t)img * T;
+    const u64* cells = cells_g + (size_t)img * PHD_CELL_Q * P.NC;
+    const int nbw = (P.nchunks + 31) / 32;
+
+    // pixel count of every group, and the image's saturation sum, from the cells
+    for (int g = tid; g < T; g += blockDim.x) n[g] = 0;
+    for (int w = tid; w < nbw; w += blockDim.x) cbits[w] = 0;
+    if (tid == 0) sh_ssum = 0;
+    __syncthreads();
+    {
+        u64 ssum = 0;
+        for (int pair = tid; pair < P.ncls * P.hp; pair += blockDim.x) {
+            u64 c = 0;
+#pragma unroll
+            for (int sub = 0; sub < 4; sub++) {
+                c += cells[pair * 4 + sub];
+                ssum += cells[3 * (size_t)P.NC + pair * 4 + sub];
+            }
+            if (c) {
+                const int cls = pair / P.hp, j = pair - cls * P.hp, spvp = P.sp * P.vp;
+                const int g = cls < spvp ? j * spvp + cls : (cls == spvp ? T - (P.vp + 1) : T - 1);
+                atomicAdd(&n[g], (int)c);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        if ((tid & 31) == 0 && ssum) atomicAdd(&sh_ssum, ssum);
+    }
+    __syncthreads();
+    if (tid == 0) iacc[img].s_sum = sh_ssum;
 
     for (int g = tid; g < T; g += blockDim.x) {
-        const int c = (int)h[g];
-        n[g] = c;
+        const int c = n[g];
+        hist[(size_t)img * T + g] = (u32)c;
         // saliency, float arithmetic in source order (:588-595)
         const float w = __fadd_rn(P.qw, __fmul_rn(P.svw, sv_f[g]));
         sal[g] = __fmul_rn(__fmul_rn((float)c, w), 1000.0f);
@@ -182,7 +215,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                     scnt[f] += 1;
                     drop += n[g] - tk - 1;
                 }
-                tie_list[(size_t)img * T + nt++] = g;
+                if (tk < n[g]) tie_list[(size_t)img * T + nt++] = g;  // partly accepted: raster order matters
             } else {
                 take[g] = -1;
                 if (pend[f] >= 0) { keep[pend[f]] = 0; drop += 1; pend[f] = -1; scnt[f] -= 1; }
@@ -198,14 +231,15 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     }
     __syncthreads();
 
-    // write the plan; tie groups locate their partial / last chunk from the per-chunk counts
+    // write the plan; partly accepted tie groups locate their partial / last chunk from the per-chunk counts and
+    // flag the chunks the tie kernel has to revisit
     for (int g = tid; g < T; g += blockDim.x) {
         GroupPlan gp;
         gp.slot = -1; gp.mode = 0; gp.cstar = -1; gp.need = 0; gp.clast = -1;
         if (slot[g] >= 0) { gp.slot = (short)slot[g]; gp.mode = 1; }
         else if (n[g] > 0 && first[g] >= 0) {
             gp.slot = (short)first[g];
-            if (take[g] < 0) gp.mode = 1;
+            if (take[g] < 0 || take[g] >= n[g]) gp.mode = 1;  // sole nearest parent, or a tie whose pixels all fit
             else {
                 gp.mode = 2;
                 const u16* cc = counts_chunk + (size_t)img * P.nchunks * T + g;
@@ -217,21 +251,46 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                     if (k == 0) continue;
                     clast = c;
                     if (!found) {
+                        atomicOr(&cbits[c >> 5], 1u << (c & 31));
                         if (cum + k >= tk) { cstar = c; need = tk - cum; found = true; }
                         cum += k;
                     }
                 }
-                if (tk >= n[g]) { cstar = P.nchunks; need = 0; }  // everything fits: accept all chunks
                 gp.cstar = cstar;
                 gp.need = need;
                 gp.clast = keep[g] ? clast : -1;
+                if (gp.clast >= 0) atomicOr(&cbits[gp.clast >> 5], 1u << (gp.clast & 31));
+                // its tie cells start from zero
+                u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
+                int c0, nc;
+                phd_group_cell_range(P, g, &c0, &nc);
+                for (int q = 0; q < PHD_CELL_Q; q++)
+                    for (int c = 0; c < nc; c++) ct[(size_t)q * P.NC + c0 + c] = 0;
             }
         }
         plan_g[(size_t)img * T + g] = gp;
+        // everything that joins a parent as a whole: fold its cells into the parent's sums
+        if (gp.mode == 1) {
+            const GroupSums S = phd_reduce_group(cells, P, g, gh[ids[gp.slot]]);
+            SlotAcc* a = sacc + (size_t)img * T + gp.slot;
+            if (S.summax) atomicAdd(&a->summax, S.summax);
+            if (S.n255) atomicAdd(&a->n255, S.n255);
+            if (S.s_sum) atomicAdd(&a->s_sum, S.s_sum);
+            if (S.t_sum) atomicAdd(&a->t_sum, (u64)S.t_sum);
+        }
     }
     for (int j = tid; j < T; j += blockDim.x) {
         parent_ids[(size_t)img * T + j] = j < N ? ids[j] : -1;
-        if (j < N) sacc[(size_t)img * T + j].cnt = (u64)scnt[j];
+        if (j < N) atomicAdd(&sacc[(size_t)img * T + j].cnt, (u64)scnt[j]);
+    }
+    __syncthreads();
+    for (int w = tid; w < nbw; w += blockDim.x) {
+        u32 bits = cbits[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            work[atomicAdd(work_n, 1u)] = (u32)img * (u32)P.nchunks + (u32)(w * 32 + b);
+        }
     }
 }
 
@@ -239,13 +298,14 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
 
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
                                cudaStream_t st, int* launches) {
-    const size_t smem = (size_t)P.T * 11 * sizeof(int);
+    const size_t smem = (size_t)P.T * 11 * sizeof(int) + (size_t)((P.nchunks + 31) / 32) * sizeof(u32);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_palette_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.hist, ws.counts_chunk, ws.plan, ws.pal_n,
-                                              ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped, ws.sacc);
+    k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.cells, ws.counts_chunk, ws.plan, ws.pal_n,
+                                              ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped, ws.sacc,
+                                              ws.hist, ws.iacc, ws.cells_tie, ws.work, ws.work_n);
     *launches += 1;
 }

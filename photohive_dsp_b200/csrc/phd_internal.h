@@ -8,16 +8,14 @@
 
 #include "photohive_dsp.h"
 
-#define PHD_CHUNK 4096        // HSV pixels per front-end chunk (one CTA iteration)
-#define PHD_FE_THREADS 256    // front-end CTA size; each thread owns PHD_CHUNK/PHD_FE_THREADS consecutive pixels
-#define PHD_PX_PER_THREAD (PHD_CHUNK / PHD_FE_THREADS)
+#define PHD_CELL_Q 5          // u64 quantities per palette cell in global memory: count, n255, sum max, sum s, sum hue fraction
 #define PHD_MAX_GROUPS 2048   // T = h*s*v + v + 1 upper bound (shared-memory tables)
 #define PHD_MAX_BINS 8192     // na*nr upper bound
 #define PHD_MAX_FACTORS 24
 
 // Fixed-point scales of the integer accumulators (all sums are exact integers => order independent).
-#define PHD_S_SHIFT 30        // saturation: s * 2^30
-#define PHD_T_SHIFT 22        // hue and wrapped hue: degrees * 2^22 (< 2^31)
+#define PHD_S_SHIFT 20        // saturation and hue fraction of the palette cells: value * 2^20
+#define PHD_T_SHIFT 22        // wrapped hue sums per parent: degrees * 2^22
 #define PHD_LN_SHIFT 20       // ln(power): value * 2^20 (value < 2^6)
 
 typedef unsigned long long u64;
@@ -30,8 +28,11 @@ struct DevParams {
     int Hp;              // column pitch of the transposed spectrum / bin map: H rounded up to a multiple of 4
     int dw, dh, ds;      // HSV (possibly downsampled) image and the rate
     long long npx, hpx;  // W*H and dw*dh
-    int nchunks;         // ceil(hpx / PHD_CHUNK)
+    int fe_threads;      // front-end CTA size (256 or 512); a chunk is fe_threads * 16 HSV pixels
+    int chunk;
+    int nchunks;         // ceil(hpx / chunk)
     int hp, sp, vp, T;
+    int ncls, NC;        // palette classes sp*vp+2 and cells ncls*hp*4 (pixel_cells.cuh)
     double Lh, Ls, Lv, bt, gt;
     double coverage;
     int L;               // linked_list_size
@@ -55,14 +56,14 @@ struct GroupPlan {
 
 // Per-parent integer accumulators (palette-accumulate -> finalize).
 struct SlotAcc {
-    u64 cnt, summax, n255, s_sum, t_sum;
+    u64 cnt, summax, n255, s_sum, t_sum;  // s_sum * 2^PHD_S_SHIFT, t_sum * 2^PHD_T_SHIFT
 };
 
 // Per-image scalar accumulators of the front end.
 struct ImageAcc {
     u64 sum[3];    // sum of k per channel
     u64 sumsq[3];  // sum of k^2 per channel
-    u64 s_sum;     // sum of s * 2^30 over the HSV image
+    u64 s_sum;     // sum of s * 2^PHD_S_SHIFT over the HSV image
     u64 pad;
 };
 
@@ -83,6 +84,10 @@ struct FftPlan {
 struct Workspace {
     int capacity;  // images
     u16* counts_chunk;   // [cap][nchunks][T]
+    u64* cells;          // [cap][PHD_CELL_Q][NC]   zeroed per sub-batch, filled by the front end
+    u64* cells_tie;      // [cap][PHD_CELL_Q][NC]   cells of the partly accepted tie groups (zeroed by palette_select)
+    u32* work;           // [cap * nchunks]         (image, chunk) items of the tie path
+    u32* work_n;         // [1]
     u32* hist;           // [cap][T]
     ImageAcc* iacc;      // [cap]
     GroupPlan* plan;     // [cap][T]
@@ -101,16 +106,18 @@ struct Workspace {
 };
 
 // ---- launchers (each in its own .cu) --------------------------------------------------------
-void phd_launch_frontend(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* pal_tables,
-                         Workspace& ws, cudaStream_t st, int* launches);
+void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                       const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches);
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
                                cudaStream_t st, int* launches);
-void phd_launch_palette_accumulate(const uint8_t* rgb, const DevParams& P, int nimg, const double* centres,
-                                   const unsigned char* pal_tables, Workspace& ws, cudaStream_t st, int* launches);
-void phd_launch_group_sweep(const DevParams& P, const unsigned char* pal_tables, bool fast, u16* out_dev,
-                            cudaStream_t st);
-void phd_launch_build_pal_tables(const DevParams& P, unsigned char* tables_dev, int* ok_dev, cudaStream_t st);
-size_t phd_pal_tables_size(int sp);
+void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                             const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches);
+void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const unsigned char* exc, bool fast,
+                            u16* out_dev, cudaStream_t st);
+void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev, unsigned char* exc_dev, int* ok_dev,
+                                  cudaStream_t st);
+size_t phd_cell_tables_size();
+size_t phd_pixels_smem(const DevParams& P);
 
 int phd_fft_plan_factors(int n, int* fac, int* nfac);  // 0 ok, nonzero unsupported
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st);

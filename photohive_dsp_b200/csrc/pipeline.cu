@@ -28,7 +28,8 @@ struct ParamTables {
     phd_params p;
     double* centres = nullptr;  // device [3*T]: group centre h, s, v
     float* sv_f = nullptr;      // device [T]: (float)(s*v) of the centre
-    unsigned char* pal = nullptr;  // device: value / saturation / reciprocal tables of hsv_fast.cuh
+    unsigned char* tabs = nullptr;  // device: class / reciprocal tables of pixel_cells.cuh
+    unsigned char* exc = nullptr;   // device: 2^24 exceptional-colour codes (pixel_cells.cuh)
 };
 
 }  // namespace
@@ -104,6 +105,17 @@ int check_params(phd_context* ctx, const phd_params* p, int max_boxes) {
     const long long T = (long long)p->h_partitions * p->s_partitions * p->v_partitions + p->v_partitions + 1;
     if (T > PHD_MAX_GROUPS) return fail(ctx, PHD_E_BAD_PARAMS, "palette grid larger than PHD_MAX_GROUPS groups");
     if (p->h_partitions > 360) return fail(ctx, PHD_E_BAD_PARAMS, "h_partitions > 360 gives a zero-width hue bin");
+    // src/color_quantization.c:41 divides 360 / h_partitions in integers; when it does not divide, the hue index
+    // reaches h_partitions and the reference writes past its group array
+    if (360 % p->h_partitions != 0)
+        return fail(ctx, PHD_E_UNSUPPORTED, "h_partitions must divide 360 (the reference overflows its group array otherwise)");
+    if ((long long)p->s_partitions * p->v_partitions + 2 > 255)
+        return fail(ctx, PHD_E_UNSUPPORTED, "s_partitions * v_partitions + 2 must fit one byte in this build");
+    {
+        const long long NC = ((long long)p->s_partitions * p->v_partitions + 2) * p->h_partitions * 4;
+        if (phd_cell_tables_size() + (size_t)NC * 44 > 200 * 1024)
+            return fail(ctx, PHD_E_UNSUPPORTED, "palette grid too fine for the shared-memory cells of this build");
+    }
     if (!(p->black_thresh >= 0.0 && p->black_thresh < 1.0 && p->gray_thresh >= 0.0 && p->gray_thresh < 1.0))
         return fail(ctx, PHD_E_BAD_PARAMS, "black_thresh and gray_thresh must lie in [0, 1)");
     if (p->radius_partitions <= 0 || p->angle_partitions <= 1 ||
@@ -124,9 +136,14 @@ void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_bo
     P.dh = P.ds > 1 ? H / P.ds : H;
     P.npx = (long long)W * H;
     P.hpx = (long long)P.dw * P.dh;
-    P.nchunks = (int)((P.hpx + PHD_CHUNK - 1) / PHD_CHUNK);
     P.hp = p.h_partitions; P.sp = p.s_partitions; P.vp = p.v_partitions;
     P.T = P.hp * P.sp * P.vp + P.vp + 1;
+    P.ncls = P.sp * P.vp + 2;
+    P.NC = P.ncls * P.hp * 4;
+    // three 256-thread CTAs per SM while the cells are small, one 512-thread CTA otherwise
+    P.fe_threads = (phd_cell_tables_size() + (size_t)P.NC * 44 <= 72 * 1024) ? 256 : 512;
+    P.chunk = P.fe_threads * 16;
+    P.nchunks = (int)((P.hpx + P.chunk - 1) / P.chunk);
     // src/color_quantization.c:41-45
     P.Lh = (double)(360 / P.hp);
     P.Ls = (1 - p.gray_thresh) / P.sp;
@@ -185,21 +202,22 @@ int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
     CUDA_TRY(ctx, cudaMalloc(&t.sv_f, sizeof(float) * T));
     CUDA_TRY(ctx, cudaMemcpyAsync(t.centres, c.data(), sizeof(double) * 3 * T, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(t.sv_f, sv.data(), sizeof(float) * T, cudaMemcpyHostToDevice, ctx->stream));
-    // fast-path tables, built on the device with the exact arithmetic
+    // per-parameter tables, built on the device with the reference's double arithmetic
     DevParams P;
     fill_dev_params(P, p, 1024, 1024, 0, 0, 0);
     int* ok_dev = nullptr;
     int ok = 1;
-    CUDA_TRY(ctx, cudaMalloc(&t.pal, phd_pal_tables_size(sp)));
+    CUDA_TRY(ctx, cudaMalloc(&t.tabs, phd_cell_tables_size()));
+    CUDA_TRY(ctx, cudaMalloc(&t.exc, (size_t)1 << 24));
     CUDA_TRY(ctx, cudaMalloc(&ok_dev, sizeof(int)));
     CUDA_TRY(ctx, cudaMemcpyAsync(ok_dev, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    phd_launch_build_pal_tables(P, t.pal, ok_dev, ctx->stream);
+    phd_launch_build_cell_tables(P, t.tabs, t.exc, ok_dev, ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(&ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ok_dev);
     if (!ok) {
-        cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.pal);
-        return fail(ctx, PHD_E_UNSUPPORTED, "saturation classes are not monotone for these thresholds");
+        cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); cudaFree(t.exc);
+        return fail(ctx, PHD_E_UNSUPPORTED, "thresholds put a colour outside the palette grid (the reference would index past it)");
     }
     ctx->tables.push_back(t);
     *out = &ctx->tables.back();
@@ -235,18 +253,21 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft) {
-    const size_t key[8] = {(size_t)cap, (size_t)P.T, (size_t)P.nchunks, (size_t)P.H, (size_t)P.fw,
+    const size_t key[8] = {(size_t)cap, (size_t)P.T * 65536 + (size_t)P.NC, (size_t)P.nchunks, (size_t)P.H, (size_t)P.fw,
                            (size_t)P.nbins, (size_t)P.max_boxes, (size_t)cap_fft};
     if (memcmp(key, ctx->ws_key, sizeof(key)) == 0 && ctx->ws.capacity == cap) return PHD_OK;
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
+    cudaFree(w.cells_tie); cudaFree(w.work);
     cudaFree(ctx->ws_zero);
     memset(&w, 0, sizeof(w));
     ctx->ws_zero = nullptr;
     const size_t T = P.T, c = cap;
     CUDA_TRY(ctx, cudaMalloc(&w.counts_chunk, sizeof(u16) * c * P.nchunks * T));
     CUDA_TRY(ctx, cudaMalloc(&w.plan, sizeof(GroupPlan) * c * T));
+    CUDA_TRY(ctx, cudaMalloc(&w.cells_tie, sizeof(u64) * c * PHD_CELL_Q * P.NC));
+    CUDA_TRY(ctx, cudaMalloc(&w.work, sizeof(u32) * c * P.nchunks));
     CUDA_TRY(ctx, cudaMalloc(&w.pal_n, sizeof(int) * c));
     CUDA_TRY(ctx, cudaMalloc(&w.parent_ids, sizeof(int) * c * T));
     CUDA_TRY(ctx, cudaMalloc(&w.tie_list, sizeof(int) * c * T));
@@ -263,6 +284,8 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft)
     const size_t o_bins = off; off = align_up(off + sizeof(u64) * c * P.nbins, 256);
     const size_t o_maxp = off; off = align_up(off + sizeof(u32) * c, 256);
     const size_t o_sharp = off; off = align_up(off + sizeof(SharpAcc) * c * (P.max_boxes > 0 ? P.max_boxes : 1), 256);
+    const size_t o_cells = off; off = align_up(off + sizeof(u64) * c * PHD_CELL_Q * P.NC, 256);
+    const size_t o_workn = off; off = align_up(off + sizeof(u32), 256);
     CUDA_TRY(ctx, cudaMalloc(&ctx->ws_zero, off));
     ctx->ws_zero_bytes = off;
     w.hist = reinterpret_cast<u32*>(ctx->ws_zero + o_hist);
@@ -271,6 +294,8 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft)
     w.binsum = reinterpret_cast<u64*>(ctx->ws_zero + o_bins);
     w.maxpow = reinterpret_cast<u32*>(ctx->ws_zero + o_maxp);
     w.sharp = reinterpret_cast<SharpAcc*>(ctx->ws_zero + o_sharp);
+    w.cells = reinterpret_cast<u64*>(ctx->ws_zero + o_cells);
+    w.work_n = reinterpret_cast<u32*>(ctx->ws_zero + o_workn);
     w.capacity = cap;
     memcpy(ctx->ws_key, key, sizeof(key));
     return PHD_OK;
@@ -395,11 +420,11 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         // records carry padding bytes no kernel writes: clear them so equal images give equal bytes
         CUDA_TRY(ctx, cudaMemsetAsync(records_dev + (size_t)first * lay.record_bytes, 0, lay.record_bytes * (size_t)n, st));
         mark(&e0);
-        phd_launch_frontend(d_in, P, n, tab->pal, ctx->ws, st, &launches);
+        phd_launch_pixels(d_in, P, n, tab->tabs, tab->exc, ctx->ws, st, &launches);
         mark(&e1); span(ST_FRONT, e0, e1); e0 = e1;
         phd_launch_palette_select(P, n, tab->centres, tab->sv_f, ctx->ws, st, &launches);
         mark(&e1); span(ST_SELECT, e0, e1); e0 = e1;
-        phd_launch_palette_accumulate(d_in, P, n, tab->centres, tab->pal, ctx->ws, st, &launches);
+        phd_launch_palette_ties(d_in, P, n, tab->tabs, tab->exc, ctx->ws, st, &launches);
         mark(&e1); span(ST_ACCUM, e0, e1); e0 = e1;
         for (int f0 = 0; f0 < n; f0 += fb) {
             const int nf = (n - f0 < fb) ? (n - f0) : fb;
@@ -515,10 +540,11 @@ void phd_context_destroy(phd_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->shapes) { cudaFree(s.tw_row); cudaFree(s.tw_col); cudaFree(s.binmap); cudaFree(s.bincount); }
-    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.pal); }
+    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); cudaFree(t.exc); }
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
+    cudaFree(w.cells_tie); cudaFree(w.work);
     cudaFree(ctx->ws_zero); cudaFree(ctx->d_rgb); cudaFree(ctx->d_records);
     for (auto e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -657,7 +683,7 @@ static int group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out, boo
     if ((rc = get_tables(ctx, *p, &tab)) != PHD_OK) return rc;
     u16* d;
     CUDA_TRY(ctx, cudaMalloc(&d, sizeof(u16) << 24));
-    phd_launch_group_sweep(P, tab->pal, fast, d, ctx->stream);
+    phd_launch_group_sweep(P, tab->tabs, tab->exc, fast, d, ctx->stream);
     cudaError_t e = cudaMemcpyAsync(out, d, sizeof(u16) << 24, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);
@@ -736,7 +762,8 @@ int phd_debug_group_counts(phd_context* ctx, const uint8_t* rgb, int width, int 
     int launches = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_rgb, rgb, tight, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, ctx->stream));
-    phd_launch_frontend(ctx->d_rgb, P, 1, tab->pal, ctx->ws, ctx->stream, &launches);
+    phd_launch_pixels(ctx->d_rgb, P, 1, tab->tabs, tab->exc, ctx->ws, ctx->stream, &launches);
+    phd_launch_palette_select(P, 1, tab->centres, tab->sv_f, ctx->ws, ctx->stream, &launches);
     CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->ws.hist, sizeof(int) * P.T, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PHD_OK;

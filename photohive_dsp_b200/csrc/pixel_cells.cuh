@@ -1,0 +1,144 @@
+// Per-pixel palette arithmetic of the single-pass front end: colour -> (cell, fixed-point h/s/v contributions).
+//
+// WHY CELLS.  The reference bins every pixel into a palette group (arm_octree, src/color_quantization.c:108-161),
+// picks parent groups, moves the other groups' pixels to their nearest parent and only then averages
+// wrap(h + 180 - h_parent), s and v per parent (calculate_avg_hsv, :510-576).  The wrap makes the hue sum depend
+// on the parent, which is unknown while the pixels stream by.  But the wrap seams sit at h_parent +- 180, and
+// group centres are bin mid-points, so every seam is a hue-bin edge or a hue-bin mid-point.  Splitting each
+// (saturation/value class, hue bin) into HALF bins therefore gives statistics from which the sums for ANY
+// parent assignment follow exactly -- one pass over the pixels, no second pass for the averages:
+//
+//     cell = ((cls * hp) + j) * 4 + sub        cls: si*vp+vi | sp*vp (gray) | sp*vp+1 (black);  j: hue bin
+//         sub 1 / 3 : lower / upper half of hue bin j (interior pixels, plus edge pixels that behave like them)
+//         sub 0     : pixels exactly on the bin's LOWER edge that belong to bin j but sit on the low side of a seam
+//         sub 2     : pixels exactly on the bin's UPPER edge that the reference's rounding put into bin j
+//                     (so that cell = cls*4hp + 2*halfbin + 1 for every ordinary pixel)
+//     per cell: count, n(max==255), sum max, sum s*2^QS, sum (h - half-bin start)/(Lh/2)*2^QS
+//
+// EXACTNESS.  hue = 60*(off + p/q) is a rational; the half-bin index is floor(num2/den) with num2 = 120*(off*q+p)
+// (+720q if negative), den = Lh*q, evaluated in FP32 on exactly representable integers (< 2^24) with a guard eps
+// that is far below the smallest possible distance 1/den of a non-integer quotient from an integer, and the
+// remainder rem = num2 - hb*den is exact.  rem != 0: the reference's double rounding (~1e-14) cannot move the pixel
+// across a half-bin boundary.  rem == 0 ("exceptional", ~2-15 % of 8-bit pixels): the pixel is exactly on a
+// boundary and the reference's IEEE-double result decides (a) its hue bin, (b) on which side of a wrap seam it
+// falls.  Both are pure functions of the 24-bit colour and h_partitions; k_build_exc evaluates the reference's
+// double arithmetic (hsv_exact.cuh) once for all 2^24 colours into a 16 MB code table that the pixel loop reads
+// for exceptional pixels only.  tests/test_gpu_parity.py sweeps all 2^24 colours against the CPU oracle.
+#pragma once
+
+#include "hsv_exact.cuh"
+
+#define PHD_TRI_SIZE 32896  // 256*257/2: (max, min) pairs with min <= max
+
+// ---- parameter tables copied to shared memory by every CTA ---------------------------------------------------
+//   svtab[tri(mx)+mn]  u8   class of the pixel from (max, min): si*vp+vi, sp*vp (gray), sp*vp+1 (black)
+//   qtab[q]            f32x2 (1/(Lh*q), Lh*q)  (q = max - min; q == 0 -> (0, 0))
+//   mtab[mx]           (f32 2^QS/mx (mx == 0 -> 0),  u32 1 + ((mx == 255) << 16))
+__host__ __device__ inline size_t phd_cell_tables_bytes() { return PHD_TRI_SIZE + 256 * 8 + 256 * 8; }
+
+struct CellTabs {
+    const unsigned char* svtab;
+    const float2* qtab;
+    const uint2* mtab;
+};
+
+__device__ __forceinline__ CellTabs phd_cell_tabs(const unsigned char* base) {
+    CellTabs t;
+    t.svtab = base;
+    t.qtab = reinterpret_cast<const float2*>(base + PHD_TRI_SIZE);
+    t.mtab = reinterpret_cast<const uint2*>(base + PHD_TRI_SIZE + 2048);
+    return t;
+}
+
+__device__ __forceinline__ void phd_cell_tabs_to_smem(unsigned char* dst, const unsigned char* __restrict__ src) {
+    const int n16 = (int)(phd_cell_tables_bytes() / 16);
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+// Constants of the pixel loop, hoisted into registers.
+struct CellCfg {
+    int hp4;        // hp * 4: cells per class
+    float eps;      // guard of the half-bin floor
+    float qscale;   // 2^QS
+    u32 sat1_bits;  // bits of MAGIC + round(0.999999 * 2^QS)
+    u32 full_bits;  // bits of MAGIC + (2^QS - 1): an edge pixel that counts as the END of its half bin
+};
+
+#define PHD_MAGIC_RN 12582912.0f   // 1.5 * 2^23: x + MAGIC has round(x) in its low mantissa bits (|x| < 2^22)
+#define PHD_MAGIC_RN_BITS 0x4B400000u
+#define PHD_MAGIC_FLOOR 8388608.0f // 2^23, added with round-down: floor(x) in the low mantissa bits (0 <= x < 2^23)
+
+__host__ __device__ inline float phd_cell_eps(int hp) { return 0.25f * (float)hp / 91800.0f; }
+
+__device__ __forceinline__ CellCfg phd_cell_cfg(const DevParams& P, int qs) {
+    CellCfg c;
+    c.hp4 = P.hp * 4;
+    c.eps = phd_cell_eps(P.hp);
+    c.qscale = (float)(1u << qs);
+    c.sat1_bits = PHD_MAGIC_RN_BITS + (u32)__double2uint_rn(0.999999 * (double)(1u << qs));
+    c.full_bits = PHD_MAGIC_RN_BITS + ((1u << qs) - 1u);
+    return c;
+}
+
+struct PixOut {
+    int cell;
+    u32 w0;      // 1 + ((max == 255) << 16)
+    u32 mx;
+    u32 sbits;   // MAGIC_BITS + s * 2^QS      (the run accumulators subtract count * MAGIC_BITS at flush time)
+    u32 hbits;   // MAGIC_BITS + fraction of the half bin * 2^QS
+};
+
+// c: the pixel as R | G << 8 | B << 16 in the low 24 bits (also the index of the exceptional-colour table); the top
+// byte may hold anything (it is the neighbouring pixel's first byte when the caller permutes packed words).
+__device__ __forceinline__ PixOut phd_pixel(u32 c, const CellTabs& T, const CellCfg& K,
+                                            const unsigned char* __restrict__ exc) {
+    PixOut o;
+    const int R = (int)(c & 255u), G = (int)((c >> 8) & 255u), B = (int)((c >> 16) & 255u);
+    const int mx = max(R, max(G, B)), mn = min(R, min(G, B));
+    const int q = mx - mn;
+    // sector with the reference's tie priority r, g, b (src/image_processing.c:394-397)
+    const bool isR = (R == mx), isG = (G == mx);
+    const int p = isR ? (G - B) : (isG ? (B - R) : (R - G));
+    const float offk = isR ? 0.0f : (isG ? 240.0f : 480.0f);
+    const float pf = (float)p, qf = (float)q;
+    float num2 = fmaf(120.0f, pf, offk * qf);          // 120 * (off*q + p), exact
+    if (num2 < 0.0f) num2 = fmaf(720.0f, qf, num2);    // h < 0 -> h + 360 (:398-404)
+    const float2 qt = T.qtab[q];
+    const uint2 mt = T.mtab[mx];
+    const int cls = T.svtab[((mx * mx + mx) >> 1) + mn];
+    // half-bin index and exact remainder
+    const float y = fmaf(num2, qt.x, K.eps);
+    const float hbm = __fadd_rd(y, PHD_MAGIC_FLOOR);
+    const int hb = (int)(__float_as_uint(hbm) & 0x7fffffu);
+    const float hbf = hbm - PHD_MAGIC_FLOOR;
+    const float rem = fmaf(-hbf, qt.y, num2);          // exact: integers below 2^24
+    const float frac = rem * qt.x;                     // in [0, 1)
+    u32 hbits = __float_as_uint(fmaf(frac, K.qscale, PHD_MAGIC_RN));
+    int cell = cls * K.hp4 + hb * 2 + 1;               // (cls*hp + (hb>>1))*4 + (hb odd ? 3 : 1)
+    if (rem == 0.0f && q != 0) {
+        // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc)
+        const int code = (int)(signed char)__ldg(exc + (c & 0x00ffffffu));
+        cell += code >> 1;
+        hbits = (code & 1) ? K.full_bits : PHD_MAGIC_RN_BITS;
+    }
+    // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
+    u32 sbits = __float_as_uint(fmaf(qf, __uint_as_float(mt.x), PHD_MAGIC_RN));
+    if (mn == 0) sbits = (mx == 0) ? PHD_MAGIC_RN_BITS : K.sat1_bits;
+    o.cell = cell;
+    o.w0 = mt.y;
+    o.mx = (u32)mx;
+    o.sbits = sbits;
+    o.hbits = hbits;
+    return o;
+}
+
+// ---- cell -> reference group id -------------------------------------------------------------------------------
+__device__ __forceinline__ int phd_cell_group(int cell, const DevParams& P) {
+    const int pair = cell >> 2;
+    const int cls = pair / P.hp, j = pair - cls * P.hp;
+    const int spvp = P.sp * P.vp;
+    if (cls < spvp) return j * spvp + cls;
+    return cls == spvp ? P.T - (P.vp + 1) : P.T - 1;
+}

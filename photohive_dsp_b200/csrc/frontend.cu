@@ -30,12 +30,9 @@ __device__ __forceinline__ u32 warp_sum_u32(u32 v) {
     return v;
 }
 
-// Pixel i (0..15) of 48 packed bytes as R | G << 8 | B << 16: one byte permute of the two words it straddles.
-__device__ __forceinline__ u32 pixel_word(const u32 (&w)[12], int i) {
-    const int byte = 3 * i, k = byte >> 2, s = byte & 3;
-    if (s == 0) return w[k] & 0x00ffffffu;
-    if (s == 1) return w[k] >> 8;
-    return __byte_perm(w[k], w[k + 1], s == 2 ? 0x7432 : 0x7543);
+// Byte b (0..47) of 48 packed bytes, zero extended: one byte permute.
+__device__ __forceinline__ int packed_byte(const u32 (&w)[12], int b) {
+    return (int)__byte_perm(w[b >> 2], 0u, 0x4440u + (u32)(b & 3));
 }
 
 // Channel sums of 16 pixels: bytes are regrouped into channel-pure words (two permutes each) and reduced with
@@ -64,20 +61,21 @@ struct CellRun {
     u32 w0, mx, s, h;
 };
 
-__device__ __forceinline__ void run_flush(uint4* chunkW, CellRun& r) {
+// chunk words are kept as four arrays of NC words (bank = cell mod 32: lanes in different cells rarely collide)
+__device__ __forceinline__ void run_flush(u32* chunkW, int NC, CellRun& r) {
     if (r.cell >= 0) {
         const u32 n = r.w0 & 0xffffu;
-        u32* c = reinterpret_cast<u32*>(chunkW + r.cell);
+        u32* c = chunkW + r.cell;
         atomicAdd(c, r.w0);
-        atomicAdd(c + 1, r.mx);
-        atomicAdd(c + 2, r.s - n * PHD_MAGIC_RN_BITS);
-        atomicAdd(c + 3, r.h - n * PHD_MAGIC_RN_BITS);
+        atomicAdd(c + NC, r.mx);
+        atomicAdd(c + 2 * NC, r.s - n * PHD_MAGIC_RN_BITS);
+        atomicAdd(c + 3 * NC, r.h - n * PHD_MAGIC_RN_BITS);
     }
 }
 
-__device__ __forceinline__ void run_add(uint4* chunkW, CellRun& r, const PixOut& o) {
+__device__ __forceinline__ void run_add(u32* chunkW, int NC, CellRun& r, const PixOut& o) {
     if (o.cell != r.cell) {
-        run_flush(chunkW, r);
+        run_flush(chunkW, NC, r);
         r.cell = o.cell; r.w0 = 0; r.mx = 0; r.s = 0; r.h = 0;
     }
     r.w0 += o.w0; r.mx += o.mx; r.s += o.sbits; r.h += o.hbits;
@@ -102,8 +100,8 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NC = P.NC;
     unsigned char* tb_raw = smem_raw;
-    uint4* chunkW = reinterpret_cast<uint4*>(smem_raw + phd_cell_tables_bytes());  // [NC]
-    u64* acc_s = reinterpret_cast<u64*>(chunkW + NC);                              // [NC]
+    u32* chunkW = reinterpret_cast<u32*>(smem_raw + phd_cell_tables_bytes());      // [4][NC]
+    u64* acc_s = reinterpret_cast<u64*>(chunkW + 4 * NC);                          // [NC]
     u64* acc_h = acc_s + NC;                                                       // [NC]
     u32* acc_cnt = reinterpret_cast<u32*>(acc_h + NC);                             // [NC]
     u32* acc_n255 = acc_cnt + NC;
@@ -114,11 +112,11 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
     phd_cell_tabs_to_smem(tb_raw, tabs_g);
     for (int i = tid; i < NC; i += THREADS) {
-        chunkW[i] = make_uint4(0, 0, 0, 0);
+        chunkW[i] = 0; chunkW[NC + i] = 0; chunkW[2 * NC + i] = 0; chunkW[3 * NC + i] = 0;
         acc_s[i] = 0; acc_h[i] = 0; acc_cnt[i] = 0; acc_n255[i] = 0; acc_mx[i] = 0;
     }
     __syncthreads();
-    const CellTabs tb = phd_cell_tabs(tb_raw);
+    const unsigned char* svtab = tb_raw;
     const CellCfg K = phd_cell_cfg(P, QS);
     const int spvp = P.sp * P.vp, hp = P.hp, npairs_colour = spvp * hp;
 
@@ -134,20 +132,24 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
                 channel_sums(w, sum, sq);  // bytes past the image end were loaded as zeros
                 if (p0 + 16 <= P.hpx) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) run_add(chunkW, run, phd_pixel(pixel_word(w, i), tb, K, exc));
-                } else {
-#pragma unroll
                     for (int i = 0; i < 16; i++)
-                        if (p0 + i < P.hpx) run_add(chunkW, run, phd_pixel(pixel_word(w, i), tb, K, exc));
+                        run_add(chunkW, NC, run, phd_pixel(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1),
+                                                           packed_byte(w, 3 * i + 2), svtab, K, exc));
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 16; i++) {
+                        if (p0 + i >= P.hpx) break;
+                        const uint8_t* q = base + (p0 + i) * 3;
+                        run_add(chunkW, NC, run, phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc));
+                    }
                 }
             } else {
                 for (int i = 0; i < 16 && p0 + i < P.hpx; i++) {
                     const uint8_t* q = base + phd_src_index(p0 + i, P) * 3;
-                    const u32 c = (u32)__ldg(q) | ((u32)__ldg(q + 1) << 8) | ((u32)__ldg(q + 2) << 16);
-                    run_add(chunkW, run, phd_pixel(c, tb, K, exc));
+                    run_add(chunkW, NC, run, phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc));
                 }
             }
-            run_flush(chunkW, run);
+            run_flush(chunkW, NC, run);
         }
         __syncthreads();
         // drain: chunk words -> running sums, per-chunk group counts (needed for raster ranks in the tie path)
@@ -157,15 +159,15 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
 #pragma unroll
             for (int sub = 0; sub < 4; sub++) {
                 const int cell = pair * 4 + sub;
-                const uint4 v = chunkW[cell];
-                if (v.x) {
-                    cnt += v.x & 0xffffu;
-                    acc_cnt[cell] += v.x & 0xffffu;
-                    acc_n255[cell] += v.x >> 16;
-                    acc_mx[cell] += v.y;
-                    acc_s[cell] += v.z;
-                    acc_h[cell] += v.w;
-                    chunkW[cell] = make_uint4(0, 0, 0, 0);
+                const u32 v0 = chunkW[cell];
+                if (v0) {
+                    cnt += v0 & 0xffffu;
+                    acc_cnt[cell] += v0 & 0xffffu;
+                    acc_n255[cell] += v0 >> 16;
+                    acc_mx[cell] += chunkW[NC + cell];
+                    acc_s[cell] += chunkW[2 * NC + cell];
+                    acc_h[cell] += chunkW[3 * NC + cell];
+                    chunkW[cell] = 0; chunkW[NC + cell] = 0; chunkW[2 * NC + cell] = 0; chunkW[3 * NC + cell] = 0;
                 }
             }
             return cnt;
@@ -262,14 +264,13 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
     if (blockIdx.x >= n_items) return;
     phd_cell_tabs_to_smem(tb_raw, tabs_g);
     __syncthreads();
-    const CellTabs tb = phd_cell_tabs(tb_raw);
-    // the tables carry 2^QS / max for the front end's QS; tie cells are kept in Q20 like the global cells
-    const int qs = (P.fe_threads == 256) ? 20 : 19;
+    const unsigned char* svtab = tb_raw;
+    const int qs = 20;  // tie cells are kept in Q20 like the global cells
     const CellCfg K = phd_cell_cfg(P, qs);
 
-    auto pixel_at = [&](const uint8_t* base, long long i) -> u32 {
+    auto pixel_at = [&](const uint8_t* base, long long i) -> PixOut {
         const uint8_t* q = base + phd_src_index(i, P) * 3;
-        return (u32)__ldg(q) | ((u32)__ldg(q + 1) << 8) | ((u32)__ldg(q + 2) << 16);
+        return phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc);
     };
     auto accept = [&](u64* ct, const PixOut& o) {
         atomicAdd(ct + o.cell, 1ull);
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
             const int li = tid * ppt + i;
             int gid = 0xffff;
             if (c0 + li < P.hpx) {
-                const PixOut o = phd_pixel(pixel_at(base, c0 + li), tb, K, exc);
+                const PixOut o = pixel_at(base, c0 + li);
                 gid = phd_cell_group(o.cell, P);
                 const GroupPlan gp = plan[gid];
                 if (gp.mode == 2 && chunk < gp.cstar) accept(ct, o);  // whole chunk accepted
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
                 if (gid_cache[li] != g) continue;
                 const bool take = (partial && rank < gp.need) || (last && li == last_idx);
                 rank++;
-                if (take) accept(ct, phd_pixel(pixel_at(base, c0 + li), tb, K, exc));
+                if (take) accept(ct, pixel_at(base, c0 + li));
             }
             __syncthreads();
         }
@@ -344,9 +345,8 @@ __global__ void __launch_bounds__(256) k_group_sweep(DevParams P, const unsigned
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;  // r<<16 | g<<8 | b
     const int R = (c >> 16) & 255, G = (c >> 8) & 255, B = c & 255;
     if (FAST) {
-        const CellTabs tb = phd_cell_tabs(tb_raw);
         const CellCfg K = phd_cell_cfg(P, 20);
-        const PixOut o = phd_pixel((u32)R | ((u32)G << 8) | ((u32)B << 16), tb, K, exc);
+        const PixOut o = phd_pixel(R, G, B, tb_raw, K, exc);
         out[c] = (u16)phd_cell_group(o.cell, P);
     } else {
         const HsvD px = phd_hsv_exact(R, G, B, k255);
@@ -355,15 +355,13 @@ __global__ void __launch_bounds__(256) k_group_sweep(DevParams P, const unsigned
 }
 
 // Per-parameter tables with the reference's arithmetic (pixel_cells.cuh); one thread per max value.
-__global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, int qs, unsigned char* __restrict__ out,
+__global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, unsigned char* __restrict__ out,
                                                            int* __restrict__ ok) {
     __shared__ double k255[256];
     phd_fill_k255(k255);
     __syncthreads();
     const int m = threadIdx.x;
     unsigned char* svtab = out;
-    float2* qtab = reinterpret_cast<float2*>(out + PHD_TRI_SIZE);
-    uint2* mtab = reinterpret_cast<uint2*>(out + PHD_TRI_SIZE + 2048);
     const int spvp = P.sp * P.vp;
     // value bin / black (rgb2hsv :408, arm_octree :129,141)
     const double v = (m == 255) ? 0.999999 : k255[m];
@@ -386,14 +384,10 @@ __global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, int qs, 
         }
         svtab[((m * m + m) >> 1) + mn] = (unsigned char)cls;
     }
-    const int Lhi = (int)P.Lh;
-    qtab[m] = m ? make_float2((float)(1.0 / (double)(Lhi * m)), (float)(Lhi * m)) : make_float2(0.f, 0.f);
-    mtab[m] = make_uint2(m ? __float_as_uint((float)((double)(1u << qs) / (double)m)) : 0u,
-                         1u + ((m == 255) ? 65536u : 0u));
 }
 
 // Exceptional-colour codes (pixel_cells.cuh): for every colour whose hue is exactly k * Lh/2, what the reference's
-// doubles make of it.  code = (cell delta << 1) | full, relative to the ordinary cell cls*4hp + 2k + 1.
+// doubles make of it.  code = ((cell delta + 4) << 1) | full, relative to the ordinary cell cls*4hp + 2k + 1.
 __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* __restrict__ out, int* __restrict__ ok) {
     __shared__ double k255[256];
     phd_fill_k255(k255);
@@ -433,17 +427,17 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
                 delta = below ? -2 : 0;  // (j, end of the lower half) | (j, upper half)
                 full = below ? 1 : 0;
             }
-            code = delta * 2 + full;
+            code = (delta + 4) * 2 + full;
         }
     }
-    out[c] = (unsigned char)(signed char)code;
+    out[c] = (unsigned char)code;
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
 size_t phd_pixels_smem(const DevParams& P) {
-    return phd_cell_tables_bytes() + (size_t)P.NC * (sizeof(uint4) + 2 * sizeof(u64) + 3 * sizeof(u32));
+    return phd_cell_tables_bytes() + (size_t)P.NC * (4 * sizeof(u32) + 2 * sizeof(u64) + 3 * sizeof(u32));
 }
 
 void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
@@ -508,7 +502,7 @@ void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const
 
 void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev, unsigned char* exc_dev, int* ok_dev,
                                   cudaStream_t st) {
-    k_build_cell_tables<<<1, 256, 0, st>>>(P, P.fe_threads == 256 ? 20 : 19, tables_dev, ok_dev);
+    k_build_cell_tables<<<1, 256, 0, st>>>(P, tables_dev, ok_dev);
     k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
 }
 

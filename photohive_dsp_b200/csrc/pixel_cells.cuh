@@ -30,25 +30,10 @@
 
 #define PHD_TRI_SIZE 32896  // 256*257/2: (max, min) pairs with min <= max
 
-// ---- parameter tables copied to shared memory by every CTA ---------------------------------------------------
+// ---- parameter table copied to shared memory by every CTA ----------------------------------------------------
 //   svtab[tri(mx)+mn]  u8   class of the pixel from (max, min): si*vp+vi, sp*vp (gray), sp*vp+1 (black)
-//   qtab[q]            f32x2 (1/(Lh*q), Lh*q)  (q = max - min; q == 0 -> (0, 0))
-//   mtab[mx]           (f32 2^QS/mx (mx == 0 -> 0),  u32 1 + ((mx == 255) << 16))
-__host__ __device__ inline size_t phd_cell_tables_bytes() { return PHD_TRI_SIZE + 256 * 8 + 256 * 8; }
-
-struct CellTabs {
-    const unsigned char* svtab;
-    const float2* qtab;
-    const uint2* mtab;
-};
-
-__device__ __forceinline__ CellTabs phd_cell_tabs(const unsigned char* base) {
-    CellTabs t;
-    t.svtab = base;
-    t.qtab = reinterpret_cast<const float2*>(base + PHD_TRI_SIZE);
-    t.mtab = reinterpret_cast<const uint2*>(base + PHD_TRI_SIZE + 2048);
-    return t;
-}
+// (reciprocals of max and of Lh*(max-min) come from MUFU.RCP: 1 ulp is ample, see phd_pixel)
+__host__ __device__ inline size_t phd_cell_tables_bytes() { return PHD_TRI_SIZE; }
 
 __device__ __forceinline__ void phd_cell_tabs_to_smem(unsigned char* dst, const unsigned char* __restrict__ src) {
     const int n16 = (int)(phd_cell_tables_bytes() / 16);
@@ -60,6 +45,7 @@ __device__ __forceinline__ void phd_cell_tabs_to_smem(unsigned char* dst, const 
 // Constants of the pixel loop, hoisted into registers.
 struct CellCfg {
     int hp4;        // hp * 4: cells per class
+    float Lh;       // hue-bin width in degrees (an integer)
     float eps;      // guard of the half-bin floor
     float qscale;   // 2^QS
     u32 sat1_bits;  // bits of MAGIC + round(0.999999 * 2^QS)
@@ -69,12 +55,16 @@ struct CellCfg {
 #define PHD_MAGIC_RN 12582912.0f   // 1.5 * 2^23: x + MAGIC has round(x) in its low mantissa bits (|x| < 2^22)
 #define PHD_MAGIC_RN_BITS 0x4B400000u
 #define PHD_MAGIC_FLOOR 8388608.0f // 2^23, added with round-down: floor(x) in the low mantissa bits (0 <= x < 2^23)
+#define PHD_MAGIC_FLOOR_BITS 0x4B000000u
 
+// A non-integer num2/den is at least 1/den >= hp/91800 away from an integer; the FP32 evaluation errs by less than
+// 2hp * 3 * 2^-24 (reciprocal 1 ulp, product, sum); eps sits a quarter of the way.
 __host__ __device__ inline float phd_cell_eps(int hp) { return 0.25f * (float)hp / 91800.0f; }
 
 __device__ __forceinline__ CellCfg phd_cell_cfg(const DevParams& P, int qs) {
     CellCfg c;
     c.hp4 = P.hp * 4;
+    c.Lh = (float)P.Lh;
     c.eps = phd_cell_eps(P.hp);
     c.qscale = (float)(1u << qs);
     c.sat1_bits = PHD_MAGIC_RN_BITS + (u32)__double2uint_rn(0.999999 * (double)(1u << qs));
@@ -90,12 +80,16 @@ struct PixOut {
     u32 hbits;   // MAGIC_BITS + fraction of the half bin * 2^QS
 };
 
-// c: the pixel as R | G << 8 | B << 16 in the low 24 bits (also the index of the exceptional-colour table); the top
-// byte may hold anything (it is the neighbouring pixel's first byte when the caller permutes packed words).
-__device__ __forceinline__ PixOut phd_pixel(u32 c, const CellTabs& T, const CellCfg& K,
-                                            const unsigned char* __restrict__ exc) {
+__device__ __forceinline__ float phd_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// exc: the 2^24 exceptional-colour codes, indexed R | G << 8 | B << 16.
+__device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned char* __restrict__ svtab,
+                                            const CellCfg& K, const unsigned char* __restrict__ exc) {
     PixOut o;
-    const int R = (int)(c & 255u), G = (int)((c >> 8) & 255u), B = (int)((c >> 16) & 255u);
     const int mx = max(R, max(G, B)), mn = min(R, min(G, B));
     const int q = mx - mn;
     // sector with the reference's tie priority r, g, b (src/image_processing.c:394-397)
@@ -105,29 +99,29 @@ __device__ __forceinline__ PixOut phd_pixel(u32 c, const CellTabs& T, const Cell
     const float pf = (float)p, qf = (float)q;
     float num2 = fmaf(120.0f, pf, offk * qf);          // 120 * (off*q + p), exact
     if (num2 < 0.0f) num2 = fmaf(720.0f, qf, num2);    // h < 0 -> h + 360 (:398-404)
-    const float2 qt = T.qtab[q];
-    const uint2 mt = T.mtab[mx];
-    const int cls = T.svtab[((mx * mx + mx) >> 1) + mn];
+    const int cls = svtab[((mx * mx + mx) >> 1) + mn];
     // half-bin index and exact remainder
-    const float y = fmaf(num2, qt.x, K.eps);
-    const float hbm = __fadd_rd(y, PHD_MAGIC_FLOOR);
-    const int hb = (int)(__float_as_uint(hbm) & 0x7fffffu);
+    const float den = fmaxf(K.Lh * qf, 1.0f);          // q == 0: num2 == 0, any positive den gives half bin 0
+    const float rden = phd_rcp(den);
+    const float y = fmaf(num2, rden, K.eps);
+    const float hbm = __fadd_rd(y, PHD_MAGIC_FLOOR);   // bits: 0x4B000000 + floor(y)
     const float hbf = hbm - PHD_MAGIC_FLOOR;
-    const float rem = fmaf(-hbf, qt.y, num2);          // exact: integers below 2^24
-    const float frac = rem * qt.x;                     // in [0, 1)
+    const float rem = fmaf(-hbf, den, num2);           // exact: integers below 2^24
+    const float frac = rem * rden;                     // in [0, 1)
     u32 hbits = __float_as_uint(fmaf(frac, K.qscale, PHD_MAGIC_RN));
-    int cell = cls * K.hp4 + hb * 2 + 1;               // (cls*hp + (hb>>1))*4 + (hb odd ? 3 : 1)
+    // cell = cls*4hp + 2*halfbin + 1, i.e. (cls*hp + (hb>>1))*4 + (hb odd ? 3 : 1)
+    int cell = cls * K.hp4 + (int)(2u * __float_as_uint(hbm) + (1u - 2u * PHD_MAGIC_FLOOR_BITS));
     if (rem == 0.0f && q != 0) {
         // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc)
-        const int code = (int)(signed char)__ldg(exc + (c & 0x00ffffffu));
-        cell += code >> 1;
-        hbits = (code & 1) ? K.full_bits : PHD_MAGIC_RN_BITS;
+        const u32 code = __ldg(exc + ((u32)R | ((u32)G << 8) | ((u32)B << 16)));
+        cell += (int)(code >> 1) - 4;
+        hbits = (code & 1u) ? K.full_bits : PHD_MAGIC_RN_BITS;
     }
     // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
-    u32 sbits = __float_as_uint(fmaf(qf, __uint_as_float(mt.x), PHD_MAGIC_RN));
+    u32 sbits = __float_as_uint(fmaf(qf * phd_rcp((float)mx), K.qscale, PHD_MAGIC_RN));
     if (mn == 0) sbits = (mx == 0) ? PHD_MAGIC_RN_BITS : K.sat1_bits;
     o.cell = cell;
-    o.w0 = mt.y;
+    o.w0 = (mx == 255) ? 0x10001u : 1u;
     o.mx = (u32)mx;
     o.sbits = sbits;
     o.hbits = hbits;

@@ -136,24 +136,46 @@ template <> struct Radix<15> : Composite<3, 5> {};
 template <> struct Radix<16> : Composite<4, 4> {};
 template <> struct Radix<25> : Composite<5, 5> {};
 
+// Per-pass twiddle tables of the compile-time plans: pass i (radix R, stride S, M = N/R butterflies) reads
+// twp[off_i + (j-1)*M + b] = exp(-2 pi i * (b - b % S) * j / N), j = 1..R-1 -- consecutive lanes read consecutive
+// entries (the plain table indexed by pps*j scatters a warp over up to 2*j cache lines).
+template <int N, int R0, int R1, int R2, int R3>
+struct PlanT {
+    static constexpr int off0 = 0;
+    static constexpr int off1 = off0 + (R0 - 1) * (N / R0);
+    static constexpr int off2 = off1 + (R1 - 1) * (N / R1);
+    static constexpr int off3 = off2 + (R2 - 1) * (N / R2);
+};
+
+// Padded layout of the first pass's input (one extra float2 every 16): the producers write 16 consecutive
+// elements per lane, and 17-element lane strides keep their 8-byte stores conflict free.
+__device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
+
 // One Stockham pass, compile-time length N, radix R, stride S (product of the radices already applied), over
 // nfft sequences laid out fstride apart in shared memory.  Reads are unit stride across lanes; the first pass
 // (S == 1) writes with stride R, which is why the plans start with an odd radix (conflict-free 8-byte stores).
-template <int N, int R, int S>
+template <int N, int R, int S, bool PADIN>
 __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
-                                       const float2* __restrict__ tw, int nfft, int fstride) {
+                                       const float2* __restrict__ twp, int nfft, int fstride_in, int fstride_out) {
     constexpr int M = N / R;
+    static_assert(!PADIN || M % 16 == 0, "padded input needs M % 16 == 0");
     const int total = nfft * M;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int f = idx / M;
         const int b = idx - f * M;
         const int q = b % S;
         const int pps = b - q;
-        const float2* a = in + f * fstride;
-        float2* y = out + f * fstride;
+        const float2* a = in + f * fstride_in;
+        float2* y = out + f * fstride_out;
         float2 x[R];
+        if (PADIN) {
+            const int b0 = pad16(b);
 #pragma unroll
-        for (int k = 0; k < R; k++) x[k] = a[b + k * M];
+            for (int k = 0; k < R; k++) x[k] = a[b0 + k * (M + M / 16)];
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; k++) x[k] = a[b + k * M];
+        }
         Radix<R>::run(x);
         if (S * R == N) {  // last pass: every twiddle is 1
 #pragma unroll
@@ -161,23 +183,26 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
         } else {
             y[R * pps + q] = x[0];
 #pragma unroll
-            for (int j = 1; j < R; j++) y[R * pps + q + j * S] = cmulf(x[j], __ldg(&tw[pps * j]));
+            for (int j = 1; j < R; j++) y[R * pps + q + j * S] = cmulf(x[j], __ldg(&twp[(j - 1) * M + b]));
         }
     }
 }
 
-// Up to four passes; R3 == 1 means a three-pass plan.  Returns the buffer holding the result.
-template <int N, int R0, int R1, int R2, int R3>
-__device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ tw, int nfft, int fstride) {
+// Up to four passes; R3 == 1 means a three-pass plan.  a: input (padded layout when PADIN), b: scratch.
+// Returns the buffer holding the result (unpadded, sequences fstride apart).
+template <int N, int R0, int R1, int R2, int R3, bool PADIN>
+__device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ twp, int nfft,
+                                             int fstride_a, int fstride) {
     static_assert(R0 * R1 * R2 * R3 == N, "radix plan does not multiply to N");
-    pass_t<N, R0, 1>(a, b, tw, nfft, fstride);
+    using PL = PlanT<N, R0, R1, R2, R3>;
+    pass_t<N, R0, 1, PADIN>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
     __syncthreads();
-    pass_t<N, R1, R0>(b, a, tw, nfft, fstride);
+    pass_t<N, R1, R0, false>(b, a, twp + PL::off1, nfft, fstride, fstride);
     __syncthreads();
-    pass_t<N, R2, R0 * R1>(a, b, tw, nfft, fstride);
+    pass_t<N, R2, R0 * R1, false>(a, b, twp + PL::off2, nfft, fstride, fstride);
     __syncthreads();
     if (R3 == 1) return b;
-    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2)>(b, a, tw, nfft, fstride);
+    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false>(b, a, twp + PL::off3, nfft, fstride, fstride);
     __syncthreads();
     return a;
 }
@@ -252,6 +277,18 @@ __global__ void k_twiddles(float2* tw, int n) {
     tw[k] = make_float2((float)c, (float)(-s));
 }
 
+// Pass tables of a compile-time plan (see PlanT): one launch per pass.
+__global__ void k_pass_twiddles(float2* out, int n, int r, int s) {
+    const int m = n / r;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (r - 1) * m) return;
+    const int j = i / m + 1, b = i - (j - 1) * m;
+    const int pps = b - b % s;
+    double sn, cs;
+    sincospi(2.0 * (double)(((long long)pps * j) % n) / (double)n, &sn, &cs);
+    out[i] = make_float2((float)cs, (float)(-sn));
+}
+
 __device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
     return 299 * (int)__ldg(p) + 587 * (int)__ldg(p + 1) + 114 * (int)__ldg(p + 2);
 }
@@ -263,30 +300,39 @@ __device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
 // ------------------------------------------------------------------------------------------
 template <int N, int R0, int R1, int R2, int R3>
 __global__ void __launch_bounds__(kRowThreads) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
-                                                        const float2* __restrict__ tw, float2* __restrict__ specT) {
+                                                        const float2* __restrict__ twp, float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);
-    float2* bufB = bufA + 2 * N;
+    constexpr int NP = N + N / 16;  // padded length
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [2][NP]  (also pass scratch: [2][N] fits)
+    float2* bufB = bufA + 2 * NP;                        // [2][N]
     const int img = blockIdx.y, r0 = 4 * blockIdx.x;
     const uint8_t* base = rgb + (size_t)img * P.image_stride + (size_t)r0 * N * 3;
-    // 4 rows x N/16 segments of 16 pixels (48 bytes = three 16-byte loads)
+    // 2 row pairs x N/16 segments of 16 pixels; one task reads the segment of BOTH rows of its pair
+    // (2 x three 16-byte loads) and stores 16 complex values (even row, odd row)
     constexpr int SEGS = N / 16;
-    for (int task = threadIdx.x; task < 4 * SEGS; task += blockDim.x) {
-        const int row = task / SEGS, seg = task - row * SEGS;
-        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)row * N * 3 + (size_t)seg * 48);
-        const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-        const u32 w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-        float* dst = reinterpret_cast<float*>(bufA + (row >> 1) * N + seg * 16) + (row & 1);
+    for (int task = threadIdx.x; task < 2 * SEGS; task += blockDim.x) {
+        const int pair = task / SEGS, seg = task - pair * SEGS;
+        const uint4* s0 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair) * N * 3 + (size_t)seg * 48);
+        const uint4* s1 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair + 1) * N * 3 + (size_t)seg * 48);
+        const uint4 a0 = __ldg(s0), b0 = __ldg(s0 + 1), c0 = __ldg(s0 + 2);
+        const uint4 a1 = __ldg(s1), b1 = __ldg(s1 + 1), c1 = __ldg(s1 + 2);
+        const u32 w0[12] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, c0.z, c0.w};
+        const u32 w1[12] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, c1.z, c1.w};
+        float2* dst = bufA + pair * NP + seg * 17;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            const int R = (w[(3 * i) >> 2] >> (8 * ((3 * i) & 3))) & 255;
-            const int G = (w[(3 * i + 1) >> 2] >> (8 * ((3 * i + 1) & 3))) & 255;
-            const int B = (w[(3 * i + 2) >> 2] >> (8 * ((3 * i + 2) & 3))) & 255;
-            dst[2 * i] = (float)(299 * R + 587 * G + 114 * B - PHD_GRAY_BIAS);
+            const int bR = 3 * i, bG = 3 * i + 1, bB = 3 * i + 2;
+            const int g0 = 299 * (int)__byte_perm(w0[bR >> 2], 0u, 0x4440u + (bR & 3)) +
+                           587 * (int)__byte_perm(w0[bG >> 2], 0u, 0x4440u + (bG & 3)) +
+                           114 * (int)__byte_perm(w0[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
+            const int g1 = 299 * (int)__byte_perm(w1[bR >> 2], 0u, 0x4440u + (bR & 3)) +
+                           587 * (int)__byte_perm(w1[bG >> 2], 0u, 0x4440u + (bG & 3)) +
+                           114 * (int)__byte_perm(w1[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
+            dst[i] = make_float2((float)g0, (float)g1);
         }
     }
     __syncthreads();
-    const float2* z = fft_run_t<N, R0, R1, R2, R3>(bufA, bufB, tw, 2, N);
+    const float2* z = fft_run_t<N, R0, R1, R2, R3, true>(bufA, bufB, twp, 2, NP, N);
     const int fw = N / 2 + 1;
     float2* out = specT + (size_t)img * fw * P.Hp + r0;
     for (int k = threadIdx.x; k < fw; k += blockDim.x) {
@@ -470,7 +516,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
         for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
     __syncthreads();  // barrier init visible to every waiter
     mbar_wait(&bar, 0);
-    const float2* res = fft_run_t<N, R0, R1, R2, R3>(bufA, bufB, tw, ncol, N);
+    const float2* res = fft_run_t<N, R0, R1, R2, R3, false>(bufA, bufB, tw, ncol, N, N);
     constexpr int SEG = (NB * N + kColThreads - 1) / kColThreads;
     cols_epilogue<WRITE_POWER, SEG>(P, img, x0, ncol, res, N, smap, N, iacc, bin_lo, bin_hi, sh_max, binsum, maxpow,
                                     power_out);
@@ -545,7 +591,7 @@ __global__ void k_bin_map(int W, int H, int Hp, int nr, int na, u16* __restrict_
 // ---- dispatch tables of the specialised shapes -------------------------------------------------
 template <int N, int R0, int R1, int R2, int R3>
 void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
-    const size_t smem = (size_t)4 * N * sizeof(float2);
+    const size_t smem = (size_t)(4 * N + 2 * (N / 16)) * sizeof(float2);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -591,6 +637,35 @@ int phd_fft_plan_factors(int n, int* fac, int* nfac) {
     return 0;
 }
 
+// Radix plans of the compile-time specialised lengths (must match the launch_*_t dispatch below).
+static bool special_radices(int n, int r[4]) {
+    static const int tab[][5] = {{1920, 15, 8, 16, 1}, {3840, 15, 16, 16, 1}, {6000, 15, 25, 16, 1},
+                                 {1080, 15, 8, 9, 1},  {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1}};
+    for (const auto& t : tab)
+        if (t[0] == n) { r[0] = t[1]; r[1] = t[2]; r[2] = t[3]; r[3] = t[4]; return true; }
+    return false;
+}
+
+size_t phd_fft_pass_table_entries(int n) {
+    int r[4];
+    if (!special_radices(n, r)) return 0;
+    size_t e = 0;
+    for (int i = 0; i < 4; i++) e += (size_t)(r[i] - 1) * (n / r[i]);
+    return e;
+}
+
+void phd_fft_fill_pass_tables(float2* dev, int n, cudaStream_t st) {
+    int r[4];
+    if (!special_radices(n, r)) return;
+    int s = 1;
+    for (int i = 0; i < 4; i++) {
+        const int cnt = (r[i] - 1) * (n / r[i]);
+        if (cnt > 0) k_pass_twiddles<<<(cnt + 255) / 256, 256, 0, st>>>(dev, n, r[i], s);
+        dev += cnt;
+        s *= r[i];
+    }
+}
+
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st) {
     k_twiddles<<<(n + 255) / 256, 256, 0, st>>>(dev_tw, n);
 }
@@ -604,9 +679,9 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
     *launches += 1;
     if (rows_fast_ok(P)) {
         switch (P.W) {
-            case 1920: launch_rows_t<1920, 15, 8, 16, 1>(rgb, P, nimg, row.tw, specT, st); return 0;
-            case 3840: launch_rows_t<3840, 15, 16, 16, 1>(rgb, P, nimg, row.tw, specT, st); return 0;
-            case 6000: launch_rows_t<6000, 15, 25, 16, 1>(rgb, P, nimg, row.tw, specT, st); return 0;
+            case 1920: launch_rows_t<1920, 15, 8, 16, 1>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 3840: launch_rows_t<3840, 15, 16, 16, 1>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 6000: launch_rows_t<6000, 15, 25, 16, 1>(rgb, P, nimg, row.twp, specT, st); return 0;
         }
     }
     const size_t smem = (size_t)P.W * 2 * sizeof(float2);
@@ -634,9 +709,9 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
     *launches += 1;
     if (P.Hp == P.H) {
         switch (P.H) {
-            case 1080: launch_cols_t<1080, 15, 8, 9, 1, 4>(P, nimg, col.tw, specT, binmapT, ws, power_out, st); return 0;
-            case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.tw, specT, binmapT, ws, power_out, st); return 0;
-            case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.tw, specT, binmapT, ws, power_out, st); return 0;
+            case 1080: launch_cols_t<1080, 15, 8, 9, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
         }
     }
     int tc;

@@ -234,17 +234,22 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
         return fail(ctx, PHD_E_UNSUPPORTED, "image side has a prime factor > 31: FFT length not supported by this build");
     const int Hp = (H + 3) / 4 * 4;
     const size_t nspec = (size_t)(W / 2 + 1) * Hp;
-    CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * W));
-    CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * H));
+    const size_t pe_row = phd_fft_pass_table_entries(W), pe_col = phd_fft_pass_table_entries(H);
+    CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * (W + pe_row)));
+    CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * (H + pe_col)));
     CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
     CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
     phd_fill_twiddles(s.tw_row, W, ctx->stream);
     phd_fill_twiddles(s.tw_col, H, ctx->stream);
+    phd_fft_fill_pass_tables(s.tw_row + W, W, ctx->stream);
+    phd_fft_fill_pass_tables(s.tw_col + H, H, ctx->stream);
     phd_launch_bin_map(W, H, Hp, nr, na, s.binmap, s.bincount, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     s.row.tw = s.tw_row;
     s.col.tw = s.tw_col;
+    s.row.twp = pe_row ? s.tw_row + W : nullptr;
+    s.col.twp = pe_col ? s.tw_col + H : nullptr;
     ctx->shapes.push_back(s);
     *out = &ctx->shapes.back();
     return PHD_OK;

@@ -214,6 +214,8 @@ PHD_API Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_
  * path, [4] row FFT, [5] column FFT + blur binning, [6] sharpness, [7] finalize.
  * Returns the number of kernel launches of that call. */
 PHD_API int phd_last_timing(const phd_context* ctx, float ms[8]);
+/* How many times each of those stages was launched in that call (sub-batches), same indexing; [0] = 1. */
+PHD_API int phd_last_stage_launches(const phd_context* ctx, int n[8]);
 
 /* Test hooks (parity tests call these through the C ABI; they are not needed by applications). */
 PHD_API int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out_2pow24 /* host */);       /* product path (integer fast path + FP64 edge path) */

@@ -156,6 +156,13 @@ class Context:
                  "sharpness", "finalize"]
         return dict(zip(names, [float(x) for x in ms])), launches
 
+    STAGES = ["total", "frontend", "palette_select", "palette_ties", "fft_rows", "fft_cols_blur", "sharpness", "finalize"]
+
+    def last_stage_launches(self):
+        n = (C.c_int * 8)()
+        self._check(lib.phd_last_stage_launches(self._h, C.byref(n)))
+        return dict(zip(self.STAGES, [int(x) for x in n]))
+
     # ---- test hooks ---------------------------------------------------------------------------------
     def debug_group_sweep(self, params: phd_params, exact: bool = False) -> np.ndarray:
         """Group id of all 2^24 colours: product path, or (exact=True) the FP64 transcription."""

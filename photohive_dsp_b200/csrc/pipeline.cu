@@ -52,6 +52,7 @@ struct phd_context {
     std::vector<int> spans;  // (stage, start event index, end event index) triples of the last call
     size_t events_used = 0;
     float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int last_stage_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int last_launches = 0;
     char err[512] = {0};
 };
@@ -395,7 +396,11 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         *idx = (int)ctx->events_used++;
         return cudaEventRecord(ctx->events[*idx], st) != cudaSuccess;
     };
-    auto span = [&](int stage, int a, int b) { ctx->spans.push_back(stage); ctx->spans.push_back(a); ctx->spans.push_back(b); };
+    for (int i = 0; i < 8; i++) ctx->last_stage_launches[i] = 0;
+    auto span = [&](int stage, int a, int b) {
+        ctx->spans.push_back(stage); ctx->spans.push_back(a); ctx->spans.push_back(b);
+        ctx->last_stage_launches[stage]++;
+    };
     int launches = 0;
     int e_begin, e_end, e0, e1;
     if (mark(&e_begin)) return fail(ctx, PHD_E_CUDA, "cudaEventRecord failed");
@@ -616,6 +621,12 @@ int phd_last_timing(const phd_context* ctx, float ms[8]) {
     if (!ctx) return 0;
     for (int i = 0; i < 8; i++) ms[i] = ctx->last_ms[i];
     return ctx->last_launches;
+}
+
+int phd_last_stage_launches(const phd_context* ctx, int n[8]) {
+    if (!ctx) return PHD_E_BAD_PARAMS;
+    for (int i = 0; i < 8; i++) n[i] = ctx->last_stage_launches[i];
+    return PHD_OK;
 }
 
 Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_flat_layout* lay) {

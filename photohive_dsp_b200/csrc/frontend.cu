@@ -54,41 +54,69 @@ __device__ __forceinline__ void channel_sums(const u32 (&w)[12], u32 (&sum)[3], 
     }
 }
 
-// Per-thread run of consecutive pixels that fall into the same cell; flushed with four native 32-bit
-// shared-memory atomics (ATOMS.ADD) when the cell changes.
+// Per-thread run of consecutive pixels that fall into the same cell.  EVERY pixel issues four native 32-bit
+// shared-memory reductions (ATOMS.ADD, no branch): when the cell changed they carry the finished run to its cell,
+// otherwise they add to a per-lane scratch cell (index NC + lane: conflict free, never read).  A branch-free loop
+// lets the scheduler overlap the 16 pixels of a thread -- with a branch per pixel the table / exceptional-colour
+// load latencies were exposed (profiles/).  sbits/hbits carry the float->int magic bias; the drain removes
+// count * bias (mod 2^32).
 struct CellRun {
-    int cell;
+    u32 addr;  // shared-space byte address of the cell's word 0
     u32 w0, mx, s, h;
 };
 
-// chunk words are kept as four arrays of NC words (bank = cell mod 32: lanes in different cells rarely collide)
-__device__ __forceinline__ void run_flush(u32* chunkW, int NC, CellRun& r) {
-    if (r.cell >= 0) {
-        const u32 n = r.w0 & 0xffffu;
-        u32* c = chunkW + r.cell;
-        atomicAdd(c, r.w0);
-        atomicAdd(c + NC, r.mx);
-        atomicAdd(c + 2 * NC, r.s - n * PHD_MAGIC_RN_BITS);
-        atomicAdd(c + 3 * NC, r.h - n * PHD_MAGIC_RN_BITS);
+// STRIDE_B > 0: compile-time byte stride between the four word arrays (immediate offsets); 0: runtime stride.
+template <int STRIDE_B>
+__device__ __forceinline__ void run_emit(u32 addr, const CellRun& r, u32 stride_b) {
+    if (STRIDE_B > 0) {
+        asm volatile(
+            "red.shared.add.u32 [%0], %1;\n\t"
+            "red.shared.add.u32 [%0+%5], %2;\n\t"
+            "red.shared.add.u32 [%0+%6], %3;\n\t"
+            "red.shared.add.u32 [%0+%7], %4;"
+            ::"r"(addr), "r"(r.w0), "r"(r.mx), "r"(r.s), "r"(r.h), "n"(STRIDE_B), "n"(2 * STRIDE_B), "n"(3 * STRIDE_B));
+    } else {
+        asm volatile(
+            "red.shared.add.u32 [%0], %1;\n\t"
+            "red.shared.add.u32 [%5], %2;\n\t"
+            "red.shared.add.u32 [%6], %3;\n\t"
+            "red.shared.add.u32 [%7], %4;"
+            ::"r"(addr), "r"(r.w0), "r"(r.mx), "r"(r.s), "r"(r.h), "r"(addr + stride_b), "r"(addr + 2 * stride_b),
+              "r"(addr + 3 * stride_b));
     }
 }
 
-__device__ __forceinline__ void run_add(u32* chunkW, int NC, CellRun& r, const PixOut& o) {
-    if (o.cell != r.cell) {
-        run_flush(chunkW, NC, r);
-        r.cell = o.cell; r.w0 = 0; r.mx = 0; r.s = 0; r.h = 0;
-    }
-    r.w0 += o.w0; r.mx += o.mx; r.s += o.sbits; r.h += o.hbits;
+template <int STRIDE_B>
+__device__ __forceinline__ void run_step(CellRun& r, u32 base, u32 scratch, u32 stride_b, const PixOut& o) {
+    const u32 addr = base + 4u * (u32)o.cell;
+    const bool change = (addr != r.addr);
+    run_emit<STRIDE_B>(change ? r.addr : scratch, r, stride_b);
+    r.w0 = (change ? 0u : r.w0) + o.w0;
+    r.mx = (change ? 0u : r.mx) + o.mx;
+    r.s = (change ? 0u : r.s) + o.sbits;
+    r.h = (change ? 0u : r.h) + o.hbits;
+    r.addr = addr;
+}
+
+__device__ __forceinline__ void load48_aligned(const uint8_t* __restrict__ p, u32 (&w)[12]) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
 }
 
 // ------------------------------------------------------------------------------------------
 // One CTA walks `cpp` consecutive chunks of one image.  A chunk is THREADS*16 HSV pixels; each thread owns 16
-// consecutive pixels (48 bytes, three 16-byte loads).  Shared memory: the parameter tables, the chunk's cell
-// words (4 x u32 per cell, fed by atomics), and the CTA's running cell sums (plain adds in the drain, one owner
+// consecutive pixels (48 bytes, three 16-byte loads, prefetched one chunk ahead).  Shared memory: the class table,
+// TWO sets of chunk cell words (4 arrays each, fed by reductions; while chunk c+1 fills one set the other is
+// drained, so there is one barrier per chunk), and the CTA's running cell sums (plain adds in the drain, one owner
 // thread per cell), flushed to the image's global cells once per CTA.
 //   chunk word 0: count | n255 << 16     1: sum max     2: sum s * 2^QS     3: sum hue fraction * 2^QS
 // QS = 32 - log2(chunk pixels), so a whole chunk cannot overflow 32 bits.
-template <int THREADS, bool DS>
+// NCS: compile-time stride (words) between the chunk word arrays, 0 = P.NC + 32 at run time.
+// DB: two chunk sets (one barrier per chunk); false = one set and a second barrier after the drain (large palettes).
+template <int THREADS, bool DS, int NCS, bool DB>
 __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ rgb, DevParams P,
                                                     const unsigned char* __restrict__ tabs_g,
                                                     const unsigned char* __restrict__ exc, int cpp,
@@ -99,75 +127,115 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     static_assert(THREADS == 256 || THREADS == 512, "chunk size / QS pairs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NC = P.NC;
+    const int ncs = NCS > 0 ? NCS : NC + 32;  // word stride of the chunk arrays (cells + 32 scratch cells)
     unsigned char* tb_raw = smem_raw;
-    u32* chunkW = reinterpret_cast<u32*>(smem_raw + phd_cell_tables_bytes());      // [4][NC]
-    u64* acc_s = reinterpret_cast<u64*>(chunkW + 4 * NC);                          // [NC]
+    u32* chunkW = reinterpret_cast<u32*>(smem_raw + phd_cell_tables_bytes());      // [DB ? 2 : 1][4][ncs]
+    u64* acc_s = reinterpret_cast<u64*>(chunkW + (DB ? 8 : 4) * ncs);              // [NC]
     u64* acc_h = acc_s + NC;                                                       // [NC]
     u32* acc_cnt = reinterpret_cast<u32*>(acc_h + NC);                             // [NC]
     u32* acc_n255 = acc_cnt + NC;
     u32* acc_mx = acc_n255 + NC;
     __shared__ u64 red[6][THREADS / 32];
+    __shared__ u32 gb[2][2];  // per chunk set: pixels of the gray and of the black group
 
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
     phd_cell_tabs_to_smem(tb_raw, tabs_g);
+    for (int i = tid; i < (DB ? 8 : 4) * ncs; i += THREADS) chunkW[i] = 0;
     for (int i = tid; i < NC; i += THREADS) {
-        chunkW[i] = 0; chunkW[NC + i] = 0; chunkW[2 * NC + i] = 0; chunkW[3 * NC + i] = 0;
         acc_s[i] = 0; acc_h[i] = 0; acc_cnt[i] = 0; acc_n255[i] = 0; acc_mx[i] = 0;
     }
+    if (tid < 4) gb[tid >> 1][tid & 1] = 0;
     __syncthreads();
     const unsigned char* svtab = tb_raw;
     const CellCfg K = phd_cell_cfg(P, QS);
     const int spvp = P.sp * P.vp, hp = P.hp, npairs_colour = spvp * hp;
+    const u32 cw_base0 = (u32)__cvta_generic_to_shared(chunkW);
+    const u32 stride_b = 4u * (u32)ncs;
+    const u32 set_b = 4u * stride_b;  // bytes between the two chunk sets
 
     u32 sum[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
     const int c_begin = blockIdx.x * cpp, c_end = min(c_begin + cpp, P.nchunks);
+    const bool fast_ok = !DS && P.aligned16 != 0;
+    u32 w[12];
+    {
+        const long long p0 = (long long)c_begin * CHUNK + (long long)tid * 16;
+        if (fast_ok && p0 + 16 <= P.hpx) load48_aligned(base + p0 * 3, w);
+    }
     for (int chunk = c_begin; chunk < c_end; chunk++) {
+        const int set = DB ? ((chunk - c_begin) & 1) : 0;
+        const u32 cw_base = cw_base0 + (u32)set * set_b;
+        const u32 scratch = cw_base + 4u * (u32)(NC + lane);
         const long long p0 = (long long)chunk * CHUNK + (long long)tid * 16;
-        if (p0 < P.hpx) {
-            CellRun run{-1, 0, 0, 0, 0};
-            if (!DS) {
-                u32 w[12];
-                phd_load48(base + p0 * 3, w, P.aligned16 != 0, (P.hpx - p0) * 3);
-                channel_sums(w, sum, sq);  // bytes past the image end were loaded as zeros
-                if (p0 + 16 <= P.hpx) {
+        if (fast_ok && p0 + 16 <= P.hpx) {
+            u32 wn[12];
+            const long long pn = p0 + CHUNK;
+            const bool more = (chunk + 1 < c_end) && (pn + 16 <= P.hpx);
+            if (more) load48_aligned(base + pn * 3, wn);  // next chunk's bytes are in flight while this one is processed
+            channel_sums(w, sum, sq);
+            CellRun run;
+            {
+                const PixOut o = phd_pixel(packed_byte(w, 0), packed_byte(w, 1), packed_byte(w, 2), svtab, K, exc);
+                run.addr = cw_base + 4u * (u32)o.cell; run.w0 = o.w0; run.mx = o.mx; run.s = o.sbits; run.h = o.hbits;
+            }
 #pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        run_add(chunkW, NC, run, phd_pixel(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1),
-                                                           packed_byte(w, 3 * i + 2), svtab, K, exc));
-                } else {
+            for (int i = 1; i < 16; i++)
+                run_step<4 * NCS>(run, cw_base, scratch, stride_b,
+                                  phd_pixel(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1), packed_byte(w, 3 * i + 2),
+                                            svtab, K, exc));
+            run_emit<4 * NCS>(run.addr, run, stride_b);
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < 12; i++) w[i] = wn[i];
+            }
+        } else if (p0 < P.hpx) {
+            // image tail, unaligned input or downsampled HSV grid: one pixel at a time
+            CellRun run{0xffffffffu, 0, 0, 0, 0};
+            bool any = false;
 #pragma unroll 1
-                    for (int i = 0; i < 16; i++) {
-                        if (p0 + i >= P.hpx) break;
-                        const uint8_t* q = base + (p0 + i) * 3;
-                        run_add(chunkW, NC, run, phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc));
-                    }
+            for (int i = 0; i < 16; i++) {
+                if (p0 + i >= P.hpx) break;
+                const uint8_t* q = base + phd_src_index(p0 + i, P) * 3;
+                const int R = __ldg(q), G = __ldg(q + 1), B = __ldg(q + 2);
+                if (!DS) {
+                    sum[0] += R; sum[1] += G; sum[2] += B;
+                    sq[0] += R * R; sq[1] += G * G; sq[2] += B * B;
                 }
-            } else {
-                for (int i = 0; i < 16 && p0 + i < P.hpx; i++) {
-                    const uint8_t* q = base + phd_src_index(p0 + i, P) * 3;
-                    run_add(chunkW, NC, run, phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc));
+                const PixOut o = phd_pixel(R, G, B, svtab, K, exc);
+                if (!any) {
+                    run.addr = cw_base + 4u * (u32)o.cell; run.w0 = o.w0; run.mx = o.mx; run.s = o.sbits; run.h = o.hbits;
+                    any = true;
+                } else {
+                    run_step<4 * NCS>(run, cw_base, scratch, stride_b, o);
                 }
             }
-            run_flush(chunkW, NC, run);
+            if (any) run_emit<4 * NCS>(run.addr, run, stride_b);
         }
-        __syncthreads();
+        __syncthreads();  // the only barrier of the chunk: set `set` is complete, the other set is free again
         // drain: chunk words -> running sums, per-chunk group counts (needed for raster ranks in the tie path)
+        u32* cw = chunkW + (size_t)set * 4 * ncs;
         u16* cc = counts_chunk + ((size_t)img * P.nchunks + chunk) * P.T;
+        if (DB && tid == 0 && chunk > c_begin) {  // gray / black totals of the PREVIOUS chunk are complete now
+            u16* ccp = cc - P.T;
+            ccp[P.T - (P.vp + 1)] = (u16)gb[set ^ 1][0];
+            ccp[P.T - 1] = (u16)gb[set ^ 1][1];
+            gb[set ^ 1][0] = 0; gb[set ^ 1][1] = 0;
+        }
         auto drain_pair = [&](int pair) -> u32 {
             u32 cnt = 0;
 #pragma unroll
             for (int sub = 0; sub < 4; sub++) {
                 const int cell = pair * 4 + sub;
-                const u32 v0 = chunkW[cell];
+                const u32 v0 = cw[cell];
                 if (v0) {
-                    cnt += v0 & 0xffffu;
-                    acc_cnt[cell] += v0 & 0xffffu;
+                    const u32 n = v0 & 0xffffu;
+                    cnt += n;
+                    acc_cnt[cell] += n;
                     acc_n255[cell] += v0 >> 16;
-                    acc_mx[cell] += chunkW[NC + cell];
-                    acc_s[cell] += chunkW[2 * NC + cell];
-                    acc_h[cell] += chunkW[3 * NC + cell];
-                    chunkW[cell] = 0; chunkW[NC + cell] = 0; chunkW[2 * NC + cell] = 0; chunkW[3 * NC + cell] = 0;
+                    acc_mx[cell] += cw[ncs + cell];
+                    acc_s[cell] += cw[2 * ncs + cell] - n * PHD_MAGIC_RN_BITS;  // mod 2^32: the true sum fits
+                    acc_h[cell] += cw[3 * ncs + cell] - n * PHD_MAGIC_RN_BITS;
+                    cw[cell] = 0; cw[ncs + cell] = 0; cw[2 * ncs + cell] = 0; cw[3 * ncs + cell] = 0;
                 }
             }
             return cnt;
@@ -176,14 +244,29 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
             const int cls = pair / hp, j = pair - cls * hp;
             cc[j * spvp + cls] = (u16)drain_pair(pair);
         }
-        if (wid < 2) {  // gray (warp 0) and black (warp 1): all hue bins collapse into one group
-            u32 cnt = 0;
-            for (int j = lane; j < hp; j += 32) cnt += drain_pair((spvp + wid) * hp + j);
-            cnt = warp_sum_u32(cnt);
-            if (lane == 0) cc[wid == 0 ? P.T - (P.vp + 1) : P.T - 1] = (u16)cnt;
+        // gray and black: all hue bins collapse into one group each; handled by the LAST threads so that the
+        // colour pairs and these spread over different warps
+        for (int k = THREADS - 1 - tid; k < 2 * hp; k += THREADS) {
+            const int which = k / hp;
+            const u32 cnt = drain_pair((spvp + which) * hp + (k - which * hp));
+            if (cnt) atomicAdd(&gb[set][which], cnt);
         }
         if (tid >= 64 && tid < 64 + P.vp - 1) cc[P.T - P.vp + (tid - 64)] = 0;  // gray groups 2.. are never used
-        __syncthreads();
+        if (!DB) {
+            __syncthreads();
+            if (tid == 0) {
+                cc[P.T - (P.vp + 1)] = (u16)gb[0][0];
+                cc[P.T - 1] = (u16)gb[0][1];
+                gb[0][0] = 0; gb[0][1] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    if (DB && tid == 0 && c_end > c_begin) {
+        const int set = (c_end - 1 - c_begin) & 1;
+        u16* cc = counts_chunk + ((size_t)img * P.nchunks + (c_end - 1)) * P.T;
+        cc[P.T - (P.vp + 1)] = (u16)gb[set][0];
+        cc[P.T - 1] = (u16)gb[set][1];
     }
 
     // flush the CTA's cell sums (Q20 in global memory whatever QS is) and the channel sums
@@ -207,7 +290,7 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
         __syncthreads();
         if (tid < 6) {
             u64 v = 0;
-            for (int w = 0; w < THREADS / 32; w++) v += red[tid][w];
+            for (int w2 = 0; w2 < THREADS / 32; w2++) v += red[tid][w2];
             ImageAcc* a = iacc + img;
             if (v) atomicAdd(tid < 3 ? &a->sum[tid] : &a->sumsq[tid - 3], v);
         }
@@ -436,8 +519,11 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
+#define PHD_NCS_SMALL 640  // compile-time chunk-array stride of the 256-thread variant (cells + 32 scratch <= 640)
+
 size_t phd_pixels_smem(const DevParams& P) {
-    return phd_cell_tables_bytes() + (size_t)P.NC * (4 * sizeof(u32) + 2 * sizeof(u64) + 3 * sizeof(u32));
+    const size_t ncs = (P.fe_threads == 256) ? PHD_NCS_SMALL : (size_t)P.NC + 32;
+    return phd_cell_tables_bytes() + (P.fe_threads == 256 ? 8 : 4) * ncs * sizeof(u32) + (size_t)P.NC * (2 * sizeof(u64) + 3 * sizeof(u32));
 }
 
 void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
@@ -445,10 +531,10 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
     const size_t smem = phd_pixels_smem(P);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_pixels<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_pixels<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_pixels<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_pixels<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<256, false, PHD_NCS_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<256, true, PHD_NCS_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<512, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_pixels<512, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     // chunks per CTA: long walks amortise the table load and the final flush; enough CTAs to fill 148 SMs
@@ -458,11 +544,11 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
     dim3 grid((P.nchunks + cpp - 1) / cpp, nimg);
     const bool ds = P.ds > 1;
     if (P.fe_threads == 256) {
-        if (ds) k_pixels<256, true><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
-        else k_pixels<256, false><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+        if (ds) k_pixels<256, true, PHD_NCS_SMALL, true><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+        else k_pixels<256, false, PHD_NCS_SMALL, true><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
     } else {
-        if (ds) k_pixels<512, true><<<grid, 512, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
-        else k_pixels<512, false><<<grid, 512, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+        if (ds) k_pixels<512, true, 0, false><<<grid, 512, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
+        else k_pixels<512, false, 0, false><<<grid, 512, smem, st>>>(rgb, P, tabs, exc, cpp, ws.counts_chunk, ws.cells, ws.iacc);
     }
     *launches += 1;
     if (ds) {

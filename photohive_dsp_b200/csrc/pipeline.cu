@@ -114,7 +114,7 @@ int check_params(phd_context* ctx, const phd_params* p, int max_boxes) {
         return fail(ctx, PHD_E_UNSUPPORTED, "s_partitions * v_partitions + 2 must fit one byte in this build");
     {
         const long long NC = ((long long)p->s_partitions * p->v_partitions + 2) * p->h_partitions * 4;
-        if (phd_cell_tables_size() + (size_t)NC * 44 > 200 * 1024)
+        if (phd_cell_tables_size() + (size_t)(NC + 32) * 16 + (size_t)NC * 28 > 200 * 1024)
             return fail(ctx, PHD_E_UNSUPPORTED, "palette grid too fine for the shared-memory cells of this build");
     }
     if (!(p->black_thresh >= 0.0 && p->black_thresh < 1.0 && p->gray_thresh >= 0.0 && p->gray_thresh < 1.0))
@@ -142,7 +142,7 @@ void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_bo
     P.ncls = P.sp * P.vp + 2;
     P.NC = P.ncls * P.hp * 4;
     // three 256-thread CTAs per SM while the cells are small, one 512-thread CTA otherwise
-    P.fe_threads = (phd_cell_tables_size() + (size_t)P.NC * 44 <= 72 * 1024) ? 256 : 512;
+    P.fe_threads = (P.NC + 32 <= 640) ? 256 : 512;  // matches PHD_NCS_SMALL in frontend.cu
     P.chunk = P.fe_threads * 16;
     P.nchunks = (int)((P.hpx + P.chunk - 1) / P.chunk);
     // src/color_quantization.c:41-45

@@ -35,6 +35,10 @@ __global__ void __launch_bounds__(256) k(u32* out, u64* gtab, int gsize) {
         if (MODE == 9) { atomicAdd(&tab[r & (TBL - 1)], 1u); atomicAdd(&tab[TBL + (r & (TBL - 1))], r & 255); }  // two tables same index
         if (MODE == 10) { acc += r; }  // baseline loop
         if (MODE == 11) atomicAdd(&tab[(r & 15) * 2], 1u);                  // 16 hot addresses (heavy same-address conflicts)
+        if (MODE == 13) atomicAdd(&tab[(gtab[it & 15] + it) & (TBL - 1)], r);                   // warp-uniform address the compiler cannot prove uniform
+        if (MODE == 14) atomicAdd(&tab[((gtab[it & 15] + it) & (TBL - 1)) ^ (lane & 1)], r);     // two addresses per warp
+        if (MODE == 15) { const u32 c = ((gtab[it & 15] + it) & 255) + (lane >> 3); atomicAdd(&tab[c], 1u); atomicAdd(&tab[c + 576], r & 255); atomicAdd(&tab[c + 1152], r); }  // 4 distinct cells per warp, 3 words
+        if (MODE == 16) { const u32 c = r & 511; atomicAdd(&tab[c], 1u); atomicAdd(&tab[c + 512], r & 255); atomicAdd(&tab[c + 1024], r); atomicAdd(&tab[c + 1536], r >> 3); }  // random cells, 4 words
         if (MODE == 12) { const u32 o = atomicAdd(&tab[r & (TBL - 1)], r << 12); if (o + (r << 12) < o) atomicAdd(&tab[TBL + (r & (TBL - 1))], 1u); }  // 64-bit by carry
     }
     __syncthreads();
@@ -76,6 +80,11 @@ int main() {
     run<4>("atomicAdd u64 shared spread", out, gtab, gsize);
     run<12>("u32 add + carry (64-bit emulation)", out, gtab, gsize);
     run<9>("2x ATOMS.ADD spread", out, gtab, gsize);
+    cudaMemset(gtab, 0, gsize * 8);
+    run<13>("ATOMS.ADD runtime warp-uniform address", out, gtab, gsize);
+    run<14>("ATOMS.ADD two addresses per warp", out, gtab, gsize);
+    run<15>("3x ATOMS, 4 cells per warp (smooth image)", out, gtab, gsize);
+    run<16>("4x ATOMS, random cells of 512 (noise image)", out, gtab, gsize);
     run<5>("lane-private LDS/add/STS", out, gtab, gsize);
     run<6>("RED.ADD u64 global spread 1M", out, gtab, gsize);
     run<7>("match.any 1024 keys", out, gtab, gsize);

@@ -411,64 +411,70 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
         : "memory");
 }
 
-// Epilogue shared by both column kernels.  res: transformed columns in shared memory (column c at res + c*cs);
+// ---- epilogue pieces shared by both column kernels ------------------------------------------------------------
+// res: transformed columns in shared memory (column c at res + c*cs), values scaled by 255000 (gray numerators);
 // map: bin ids of the same columns (shared or global, column c at map + c*ms).
-template <bool WRITE_POWER, int SEG>
-__device__ __forceinline__ void cols_epilogue(const DevParams& P, int img, int x0, int ncol, const float2* res, int cs,
-                                              const u16* map, int ms, const ImageAcc* __restrict__ iacc,
-                                              u32* bin_lo, u32* bin_hi, float* sh_max, u64* __restrict__ binsum,
-                                              u32* __restrict__ maxpow, float* __restrict__ power_out) {
-    const int H = P.H;
-    const float inv_scale2 = (float)(1.0 / (255000.0 * 255000.0));
+#define PHD_POWER_SCALE (255000.0 * 255000.0)
+
+// DC coefficient: the transform ran on gray - 0.5; the reference transforms gray - (Br+Bg+Bb)/3
+// (interface.c:78, blur_profile.c:233-238).  By linearity only X[0,0] differs; it is rebuilt from the exact channel
+// sums and stored so that the common power arithmetic below reproduces it.
+__device__ __forceinline__ void cols_fix_dc(const DevParams& P, const ImageAcc* __restrict__ iacc, int img, float2* res00) {
+    const ImageAcc a = iacc[img];
+    const double np = (double)P.npx;
+    const double avg = ((double)a.sum[0] / 255.0 / np + (double)a.sum[1] / 255.0 / np + (double)a.sum[2] / 255.0 / np) / 3.0;
+    const double gsum = (299.0 * (double)a.sum[0] + 587.0 * (double)a.sum[1] + 114.0 * (double)a.sum[2]) / 255000.0;
+    const double dc = gsum - np * avg;
+    *res00 = make_float2((float)(dc * 255000.0), 0.f);
+}
+
+// power -> (p < 1 ? 0 : ln p) as fixed point 2^-20 -> polar bin, run-length merged per thread (bins change slowly
+// along a column) into the shared integer bins.  Returns the running max of the RAW power (re^2 + im^2).
+template <int SEG>
+__device__ __forceinline__ float cols_accumulate(int H, int ncol, const float2* res, int cs, const u16* map, int ms,
+                                                 u32* bin_lo, u32* bin_hi, float mymax) {
+    const float thr = (float)PHD_POWER_SCALE;                            // p >= 1  <=>  raw >= 255000^2
+    const float lg2c = (float)(-2.0 * 17.960137721520944);               // log2(1 / 255000^2)
+    const float kq = (float)(0.69314718055994530942 * (1 << PHD_LN_SHIFT));  // ln 2 * 2^20
     const int segs = (H + SEG - 1) / SEG;
-    float mymax = 0.f;
     for (int task = threadIdx.x; task < ncol * segs; task += blockDim.x) {
         const int c = task / segs, k0 = (task - c * segs) * SEG;
-        const int x = x0 + c;
+        const float2* rp = res + c * cs + k0;
+        const u16* mp = map + c * ms + k0;
         int run_bin = -1;
         u32 run_sum = 0;
 #pragma unroll
         for (int i = 0; i < SEG; i++) {
-            const int k = k0 + i;
-            if (k < H) {
-                const float2 v = res[c * cs + k];
-                float p = (v.x * v.x + v.y * v.y) * inv_scale2;
-                if (WRITE_POWER) {
-                    power_out[((size_t)img * H + k) * P.fw + x] = p;
-                } else {
-                    if (x == 0 && k == 0) {
-                        // DC: sum(gray - avg) from the exact channel sums (interface.c:78, blur_profile.c:233-238)
-                        const ImageAcc a = iacc[img];
-                        const double np = (double)P.npx;
-                        const double avg = ((double)a.sum[0] / 255.0 / np + (double)a.sum[1] / 255.0 / np +
-                                            (double)a.sum[2] / 255.0 / np) / 3.0;
-                        const double gsum = (299.0 * (double)a.sum[0] + 587.0 * (double)a.sum[1] + 114.0 * (double)a.sum[2]) / 255000.0;
-                        const double dc = gsum - np * avg;
-                        p = (float)(dc * dc);
-                    }
-                    mymax = fmaxf(mymax, p);
-                    if (p >= 1.0f) {
-                        const u32 q = (u32)__float2int_rn(__logf(p) * (float)(1 << PHD_LN_SHIFT));
-                        const int bin = map[c * ms + k];
-                        if (bin != run_bin) {
-                            if (run_sum) {
-                                atomicAdd(&bin_lo[run_bin], run_sum & 0x1fffu);
-                                atomicAdd(&bin_hi[run_bin], run_sum >> 13);
-                            }
-                            run_bin = bin;
-                            run_sum = 0;
+            if (k0 + i < H) {
+                const float2 v = rp[i];
+                const float raw = fmaf(v.x, v.x, v.y * v.y);
+                mymax = fmaxf(mymax, raw);
+                if (raw >= thr) {
+                    const u32 q = (u32)__float2int_rn((__log2f(raw) + lg2c) * kq);
+                    const int bin = mp[i];
+                    if (bin != run_bin) {
+                        if (run_sum) {
+                            atomicAdd(&bin_lo[run_bin], run_sum & 0x1fffu);
+                            atomicAdd(&bin_hi[run_bin], run_sum >> 13);
                         }
-                        run_sum += q;
+                        run_bin = bin;
+                        run_sum = 0;
                     }
+                    run_sum += q;
                 }
             }
         }
-        if (!WRITE_POWER && run_sum) {
+        if (run_sum) {
             atomicAdd(&bin_lo[run_bin], run_sum & 0x1fffu);
             atomicAdd(&bin_hi[run_bin], run_sum >> 13);
         }
     }
-    if (WRITE_POWER) return;
+    return mymax;
+}
+
+// One flush per CTA: max power (scaled to p) and the shared bins into the image's 64-bit global bins.
+__device__ __forceinline__ void cols_flush(const DevParams& P, int img, float mymax, const u32* bin_lo, const u32* bin_hi,
+                                           float* sh_max, u64* __restrict__ binsum, u32* __restrict__ maxpow) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mymax = fmaxf(mymax, __shfl_xor_sync(0xffffffffu, mymax, o));
     if ((threadIdx.x & 31) == 0) sh_max[threadIdx.x >> 5] = mymax;
@@ -476,7 +482,7 @@ __device__ __forceinline__ void cols_epilogue(const DevParams& P, int img, int x
     if (threadIdx.x == 0) {
         float m = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, sh_max[w]);
-        atomicMax(&maxpow[img], __float_as_uint(m));
+        atomicMax(&maxpow[img], __float_as_uint(m * (float)(1.0 / PHD_POWER_SCALE)));
     }
     u64* dst = binsum + (size_t)img * P.nbins;
     for (int b = threadIdx.x; b < P.nbins; b += blockDim.x) {
@@ -485,41 +491,75 @@ __device__ __forceinline__ void cols_epilogue(const DevParams& P, int img, int x
     }
 }
 
-// Columns, specialised: NB contiguous columns per CTA, staged by the bulk-copy engine.
-// Requires Hp == N (H % 4 == 0) so that columns and bin-map slices are 16-byte multiples.
+// test hook: the power spectrum itself, row major
+__device__ __forceinline__ void cols_write_power(const DevParams& P, int img, int x0, int ncol, const float2* res, int cs,
+                                                 float* __restrict__ power_out) {
+    const float inv_scale2 = (float)(1.0 / PHD_POWER_SCALE);
+    for (int idx = threadIdx.x; idx < ncol * P.H; idx += blockDim.x) {
+        const int c = idx / P.H, k = idx - c * P.H;
+        const float2 v = res[c * cs + k];
+        power_out[((size_t)img * P.H + k) * P.fw + x0 + c] = (v.x * v.x + v.y * v.y) * inv_scale2;
+    }
+}
+
+// Columns, specialised.  A CTA walks `gpc` consecutive groups of NB contiguous columns of ONE image: the shared
+// bins are zeroed and flushed once per CTA, and while a group's epilogue runs the bulk-copy engine already
+// fetches the next group's columns (into the buffer the last FFT pass no longer reads) and bin-id slices.
+// Requires Hp == N (H % 4 == 0) so that columns and bin-map slices are 16-byte multiples, and a 3-pass plan.
 template <int N, int R0, int R1, int R2, int R3, int NB, bool WRITE_POWER>
 __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float2* __restrict__ tw,
                                                         const float2* __restrict__ specT,
                                                         const u16* __restrict__ binmapT,
                                                         const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
-                                                        u32* __restrict__ maxpow, float* __restrict__ power_out) {
+                                                        u32* __restrict__ maxpow, float* __restrict__ power_out, int gpc) {
+    static_assert(R3 == 1, "the prefetch below assumes the result lands in bufB");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + NB * N;
-    u16* smap = reinterpret_cast<u16*>(bufB + NB * N);
-    u32* bin_lo = reinterpret_cast<u32*>(smap + NB * N);
+    u16* smap = reinterpret_cast<u16*>(bufB + NB * N);  // [2][NB*N]
+    u32* bin_lo = reinterpret_cast<u32*>(smap + 2 * NB * N);
     u32* bin_hi = bin_lo + P.nbins;
     __shared__ __align__(8) u64 bar;
     __shared__ float sh_max[kColThreads / 32];
 
     const int img = blockIdx.y;
-    const int x0 = blockIdx.x * NB;
-    const int ncol = min(NB, P.fw - x0);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+    const int ngroups = (P.fw + NB - 1) / NB;
+    const int g_begin = blockIdx.x * gpc, g_end = min(g_begin + gpc, ngroups);
+    auto fetch = [&](int g, int slot) {  // thread 0 only
+        const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         const u32 cbytes = (u32)(ncol * N * sizeof(float2)), mbytes = (u32)(ncol * N * sizeof(u16));
         mbar_expect_tx(&bar, cbytes + mbytes);
         bulk_g2s(bufA, specT + ((size_t)img * P.fw + x0) * N, cbytes, &bar);
-        bulk_g2s(smap, binmapT + (size_t)x0 * N, mbytes, &bar);
+        bulk_g2s(smap + slot * NB * N, binmapT + (size_t)x0 * N, mbytes, &bar);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fetch(g_begin, 0);
     }
     if (!WRITE_POWER)
         for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
     __syncthreads();  // barrier init visible to every waiter
-    mbar_wait(&bar, 0);
-    const float2* res = fft_run_t<N, R0, R1, R2, R3, false>(bufA, bufB, tw, ncol, N, N);
-    constexpr int SEG = (NB * N + kColThreads - 1) / kColThreads;
-    cols_epilogue<WRITE_POWER, SEG>(P, img, x0, ncol, res, N, smap, N, iacc, bin_lo, bin_hi, sh_max, binsum, maxpow,
-                                    power_out);
+    float mymax = 0.f;
+    for (int g = g_begin; g < g_end; g++) {
+        const int it = g - g_begin;
+        const int x0 = g * NB, ncol = min(NB, P.fw - x0);
+        mbar_wait(&bar, it & 1);
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false>(bufA, bufB, tw, ncol, N, N);  // ends with a CTA barrier
+        if (threadIdx.x == 0) {
+            if (g + 1 < g_end) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // bufA was written by pass 2
+                fetch(g + 1, (it + 1) & 1);
+            }
+            if (!WRITE_POWER && x0 == 0) cols_fix_dc(P, iacc, img, res);  // thread 0 also owns point (0,0) below
+        }
+        if (WRITE_POWER) cols_write_power(P, img, x0, ncol, res, N, power_out);
+        else {
+            constexpr int SEG = (NB * N + kColThreads - 1) / kColThreads;
+            mymax = cols_accumulate<SEG>(P.H, ncol, res, N, smap + (it & 1) * NB * N, N, bin_lo, bin_hi, mymax);
+        }
+        __syncthreads();  // bufB is rewritten by the next group's first pass
+    }
+    if (!WRITE_POWER) cols_flush(P, img, mymax, bin_lo, bin_hi, sh_max, binsum, maxpow);
 }
 
 // Columns, generic: runtime radix plan, plain loads, bin ids read from global memory.
@@ -531,7 +571,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_generic(DevParams P, FftPl
                                                               u64* __restrict__ binsum, u32* __restrict__ maxpow,
                                                               float* __restrict__ power_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int H = P.H, Hp = P.Hp;
+    const int Hp = P.Hp;
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + (size_t)TC * Hp;
     u32* bin_lo = reinterpret_cast<u32*>(bufB + (size_t)TC * Hp);
@@ -546,10 +586,15 @@ __global__ void __launch_bounds__(kColThreads) k_cols_generic(DevParams P, FftPl
         for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
     for (int idx = threadIdx.x; idx < ncol * Hp; idx += blockDim.x) bufA[idx] = src[idx];
     __syncthreads();
-    const float2* res = fft_run_rt(pl, bufA, bufB, ncol, Hp);
-    (void)H;
-    cols_epilogue<WRITE_POWER, 8>(P, img, x0, ncol, res, Hp, binmapT + (size_t)x0 * Hp, Hp, iacc, bin_lo, bin_hi,
-                                  sh_max, binsum, maxpow, power_out);
+    float2* res = fft_run_rt(pl, bufA, bufB, ncol, Hp);
+    if (WRITE_POWER) {
+        cols_write_power(P, img, x0, ncol, res, Hp, power_out);
+        return;
+    }
+    if (x0 == 0 && threadIdx.x == 0) cols_fix_dc(P, iacc, img, res);  // thread 0 also owns point (0,0) below
+    const float mymax = cols_accumulate<8>(P.H, ncol, res, Hp, binmapT + (size_t)x0 * Hp, Hp, bin_lo, bin_hi, 0.f);
+    __syncthreads();
+    cols_flush(P, img, mymax, bin_lo, bin_hi, sh_max, binsum, maxpow);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -603,18 +648,30 @@ void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float
 template <int N, int R0, int R1, int R2, int R3, int NB>
 void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
                    Workspace& ws, float* power_out, cudaStream_t st) {
-    const size_t smem = (size_t)2 * NB * N * sizeof(float2) + (size_t)NB * N * sizeof(u16) + (size_t)2 * P.nbins * sizeof(u32);
+    const size_t smem = (size_t)2 * NB * N * sizeof(float2) + (size_t)2 * NB * N * sizeof(u16) + (size_t)2 * P.nbins * sizeof(u32);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_cols_t<N, R0, R1, R2, R3, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_cols_t<N, R0, R1, R2, R3, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
-    dim3 grid((P.fw + NB - 1) / NB, nimg);
+    // groups per CTA: long walks amortise the bin zero/flush; pick the walk length whose CTA count fills whole
+    // waves of the machine (2 CTAs of this size per SM, 148 SMs)
+    const int ngroups = (P.fw + NB - 1) / NB;
+    const int slots = 2 * 148;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int gpc = 1; gpc <= 16 && gpc <= ngroups; gpc++) {
+        const long long ctas = (long long)((ngroups + gpc - 1) / gpc) * nimg;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (gpc + 0.8);  // 0.8 group-equivalents of per-CTA overhead
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = gpc; }
+    }
+    dim3 grid((ngroups + best - 1) / best, nimg);
     if (power_out)
-        k_cols_t<N, R0, R1, R2, R3, NB, true><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out);
+        k_cols_t<N, R0, R1, R2, R3, NB, true><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out, best);
     else
-        k_cols_t<N, R0, R1, R2, R3, NB, false><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr);
+        k_cols_t<N, R0, R1, R2, R3, NB, false><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr, best);
 }
 
 }  // namespace

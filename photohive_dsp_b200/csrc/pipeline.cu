@@ -326,16 +326,16 @@ bool is_device_pointer(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// Images per FFT sub-batch: the row-transformed spectra of one sub-batch should stay L2 resident
-// between the row and the column kernel (L2 is 126 MB on B200).
+// Images per FFT sub-batch (the row-transformed spectra of one sub-batch live in `spec`).  Measured on B200
+// (profiles/): bigger launches win over keeping the spectra L2 resident (48.4 k images/s at 48 images per launch,
+// 50.5 k at 512 vs 45.9 k at 11), so the sub-batch is the whole palette batch, capped at 8 GB of spectra.
 int pick_fft_batch(const DevParams& P, int n_images) {
     const char* env = getenv("PHD_SUB_BATCH");
     long long sub = env ? atoll(env) : 0;
     if (sub <= 0) {
-        const double per = (double)P.H * P.fw * sizeof(float2);
-        sub = (long long)(96.0 * 1024 * 1024 / per);
+        const double per = (double)P.Hp * P.fw * sizeof(float2);
+        sub = (long long)(8.0e9 / per);
         if (sub < 1) sub = 1;
-        if (sub > 64) sub = 64;
     }
     if (sub > n_images) sub = n_images;
     return (int)sub;

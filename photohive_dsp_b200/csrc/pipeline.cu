@@ -46,6 +46,12 @@ struct phd_context {
     size_t ws_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned char* d_rgb = nullptr;
     size_t d_rgb_bytes = 0;
+    // host input: two staging buffers filled by a copy stream while the previous sub-batch computes
+    cudaStream_t copy_stream = nullptr;
+    unsigned char* d_stage[2] = {nullptr, nullptr};
+    size_t d_stage_bytes[2] = {0, 0};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
     unsigned char* d_records = nullptr;
     size_t d_records_bytes = 0;
     std::vector<cudaEvent_t> events;
@@ -347,7 +353,7 @@ int pick_palette_batch(const DevParams& P, int n_images, bool host_input) {
     const char* env = getenv("PHD_PALETTE_BATCH");
     long long pb = env ? atoll(env) : 0;
     if (pb <= 0) {
-        pb = host_input ? 128 : 512;
+        pb = host_input ? 32 : 512;  // host input: small sub-batches keep the copy engine and the SMs both busy
         const double per = (double)P.nchunks * P.T * sizeof(u16);
         const long long cap = (long long)(1024.0 * 1024 * 1024 / per);
         if (pb > cap) pb = cap;
@@ -379,7 +385,9 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
     const int pb = pick_palette_batch(P, n_images, !input_on_device);
     const int fb = pick_fft_batch(P, pb);
     if ((rc = ensure_workspace(ctx, P, pb, fb)) != PHD_OK) return rc;
-    if (!input_on_device && (rc = ensure_bytes(ctx, &ctx->d_rgb, &ctx->d_rgb_bytes, dev_stride * pb)) != PHD_OK) return rc;
+    if (!input_on_device)
+        for (int b = 0; b < 2; b++)
+            if ((rc = ensure_bytes(ctx, &ctx->d_stage[b], &ctx->d_stage_bytes[b], dev_stride * pb)) != PHD_OK) return rc;
     int tc;
     if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
         return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
@@ -404,14 +412,32 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
     int launches = 0;
     int e_begin, e_end, e0, e1;
     if (mark(&e_begin)) return fail(ctx, PHD_E_CUDA, "cudaEventRecord failed");
-    for (int first = 0; first < n_images; first += pb) {
+    // host input: sub-batch i+1 is copied (copy stream) while sub-batch i computes
+    auto stage_copy = [&](int first, int slot, bool wait_consumed) -> cudaError_t {
+        const int n = (n_images - first < pb) ? (n_images - first) : pb;
+        cudaError_t e = cudaSuccess;
+        if (wait_consumed) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(ctx->d_stage[slot], dev_stride, rgb_host_or_dev + (size_t)first * image_stride,
+                                  image_stride, tight, n, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream);
+        return e;
+    };
+    if (!input_on_device) {
+        // order the copy stream after whatever this context did before (the staging buffers are reused)
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_consumed[0], st));
+        CUDA_TRY(ctx, stage_copy(0, 0, true));
+    }
+    int batch_index = 0;
+    for (int first = 0; first < n_images; first += pb, batch_index++) {
         const int n = (n_images - first < pb) ? (n_images - first) : pb;
         const uint8_t* d_in;
         if (input_on_device) d_in = rgb_host_or_dev + (size_t)first * image_stride;
         else {
-            CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->d_rgb, dev_stride, rgb_host_or_dev + (size_t)first * image_stride,
-                                            image_stride, tight, n, cudaMemcpyHostToDevice, st));
-            d_in = ctx->d_rgb;
+            const int slot = batch_index & 1;
+            if (first + pb < n_images) CUDA_TRY(ctx, stage_copy(first + pb, slot ^ 1, batch_index >= 1));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[slot], 0));
+            d_in = ctx->d_stage[slot];
         }
         int max_w = 0, max_h = 0;
         if (max_boxes > 0) {
@@ -454,6 +480,7 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         phd_launch_finalize(P, n, tab->centres, shape->bincount, ctx->ws, lay,
                             records_dev + (size_t)first * lay.record_bytes, st, &launches);
         mark(&e1); span(ST_FINAL, e0, e1);
+        if (!input_on_device) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_consumed[batch_index & 1], st));
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (mark(&e_end)) return fail(ctx, PHD_E_CUDA, "cudaEventRecord failed");
@@ -534,8 +561,13 @@ int phd_context_create(int device, phd_context** out) {
     }
     phd_context* ctx = new phd_context();
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int b = 0; ok && b < 2; b++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         fprintf(stderr, "photohive_dsp: cannot initialise CUDA device %d: %s\n", device,
                 cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -556,7 +588,13 @@ void phd_context_destroy(phd_context* ctx) {
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
     cudaFree(w.cells_tie); cudaFree(w.work);
     cudaFree(ctx->ws_zero); cudaFree(ctx->d_rgb); cudaFree(ctx->d_records);
+    cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     for (auto e : ctx->events) cudaEventDestroy(e);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+        if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

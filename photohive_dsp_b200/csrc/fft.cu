@@ -298,57 +298,77 @@ __device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
 // spectrum column x, the four consecutive entries specT[x][4j..4j+3] as one 32-byte sector.
 // Requires W % 16 == 0, H % 4 == 0, 16-byte aligned rows.
 // ------------------------------------------------------------------------------------------
-template <int N, int R0, int R1, int R2, int R3>
-__global__ void __launch_bounds__(kRowThreads) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
-                                                        const float2* __restrict__ twp, float2* __restrict__ specT) {
+template <int N, int R0, int R1, int R2, int R3, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
+                                                        const float2* __restrict__ twp, float2* __restrict__ specT,
+                                                        int qpc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = N + N / 16;  // padded length
     float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [2][NP]  (also pass scratch: [2][N] fits)
     float2* bufB = bufA + 2 * NP;                        // [2][N]
-    const int img = blockIdx.y, r0 = 4 * blockIdx.x;
-    const uint8_t* base = rgb + (size_t)img * P.image_stride + (size_t)r0 * N * 3;
-    // 2 row pairs x N/16 segments of 16 pixels; one task reads the segment of BOTH rows of its pair
-    // (2 x three 16-byte loads) and stores 16 complex values (even row, odd row)
+    const int img = blockIdx.y;
+    const int nquads = P.H / 4;
+    // quads blockIdx.x, blockIdx.x + gridDim.x, ...: CTAs that run together work on neighbouring rows, so the
+    // 32-byte sectors they write into the same 128-byte lines of the transposed spectrum meet in L2
+    const int q_begin = blockIdx.x, q_end = nquads, q_step = gridDim.x;
+    (void)qpc;
+    const uint8_t* img_base = rgb + (size_t)img * P.image_stride;
+    // A CTA walks qpc consecutive row quads.  Per quad: 2 row pairs x N/16 segments of 16 pixels; one task (thread)
+    // holds the segment of BOTH rows of its pair (2 x three 16-byte loads).  The loads of quad q+1 are issued
+    // before the passes of quad q and stay in registers meanwhile.
     constexpr int SEGS = N / 16;
-    for (int task = threadIdx.x; task < 2 * SEGS; task += blockDim.x) {
-        const int pair = task / SEGS, seg = task - pair * SEGS;
+    static_assert(2 * SEGS <= THREADS, "one staging task per thread");
+    const int task = threadIdx.x;
+    const bool has_task = task < 2 * SEGS;
+    const int pair = task / SEGS, seg = task - pair * SEGS;
+    uint4 a0, b0, c0, a1, b1, c1;
+    auto load_quad = [&](int q) {
+        const uint8_t* base = img_base + (size_t)(4 * q) * N * 3;
         const uint4* s0 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair) * N * 3 + (size_t)seg * 48);
         const uint4* s1 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair + 1) * N * 3 + (size_t)seg * 48);
-        const uint4 a0 = __ldg(s0), b0 = __ldg(s0 + 1), c0 = __ldg(s0 + 2);
-        const uint4 a1 = __ldg(s1), b1 = __ldg(s1 + 1), c1 = __ldg(s1 + 2);
-        const u32 w0[12] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, c0.z, c0.w};
-        const u32 w1[12] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, c1.z, c1.w};
-        float2* dst = bufA + pair * NP + seg * 17;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int bR = 3 * i, bG = 3 * i + 1, bB = 3 * i + 2;
-            const int g0 = 299 * (int)__byte_perm(w0[bR >> 2], 0u, 0x4440u + (bR & 3)) +
-                           587 * (int)__byte_perm(w0[bG >> 2], 0u, 0x4440u + (bG & 3)) +
-                           114 * (int)__byte_perm(w0[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
-            const int g1 = 299 * (int)__byte_perm(w1[bR >> 2], 0u, 0x4440u + (bR & 3)) +
-                           587 * (int)__byte_perm(w1[bG >> 2], 0u, 0x4440u + (bG & 3)) +
-                           114 * (int)__byte_perm(w1[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
-            dst[i] = make_float2((float)g0, (float)g1);
-        }
-    }
-    __syncthreads();
-    const float2* z = fft_run_t<N, R0, R1, R2, R3, true>(bufA, bufB, twp, 2, NP, N);
+        a0 = __ldg(s0); b0 = __ldg(s0 + 1); c0 = __ldg(s0 + 2);
+        a1 = __ldg(s1); b1 = __ldg(s1 + 1); c1 = __ldg(s1 + 2);
+    };
+    if (has_task && q_begin < q_end) load_quad(q_begin);
     const int fw = N / 2 + 1;
-    float2* out = specT + (size_t)img * fw * P.Hp + r0;
-    for (int k = threadIdx.x; k < fw; k += blockDim.x) {
-        const int kc = k == 0 ? 0 : N - k;
-        float4 lo, hi;
-        {
-            const float2 zk = z[k], zc = z[kc];
-            lo = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+    for (int q = q_begin; q < q_end; q += q_step) {
+        if (has_task) {
+            const u32 w0[12] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, c0.z, c0.w};
+            const u32 w1[12] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, c1.z, c1.w};
+            float2* dst = bufA + pair * NP + seg * 17;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int bR = 3 * i, bG = 3 * i + 1, bB = 3 * i + 2;
+                const int g0 = 299 * (int)__byte_perm(w0[bR >> 2], 0u, 0x4440u + (bR & 3)) +
+                               587 * (int)__byte_perm(w0[bG >> 2], 0u, 0x4440u + (bG & 3)) +
+                               114 * (int)__byte_perm(w0[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
+                const int g1 = 299 * (int)__byte_perm(w1[bR >> 2], 0u, 0x4440u + (bR & 3)) +
+                               587 * (int)__byte_perm(w1[bG >> 2], 0u, 0x4440u + (bG & 3)) +
+                               114 * (int)__byte_perm(w1[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
+                dst[i] = make_float2((float)g0, (float)g1);
+            }
+            if (q + q_step < q_end) load_quad(q + q_step);
         }
-        {
-            const float2 zk = z[N + k], zc = z[N + kc];
-            hi = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+        __syncthreads();
+        const float2* z = fft_run_t<N, R0, R1, R2, R3, true>(bufA, bufB, twp, 2, NP, N);
+        float2* out = specT + (size_t)img * fw * P.Hp + 4 * q;
+        for (int k = threadIdx.x; k < fw; k += blockDim.x) {
+            const int kc = k == 0 ? 0 : N - k;
+            float4 lo, hi;
+            {
+                const float2 zk = z[k], zc = z[kc];
+                lo = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            }
+            {
+                const float2 zk = z[N + k], zc = z[N + kc];
+                hi = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            }
+            float4* o = reinterpret_cast<float4*>(out + (size_t)k * P.Hp);
+            o[0] = lo;
+            o[1] = hi;
         }
-        float4* o = reinterpret_cast<float4*>(out + (size_t)k * P.Hp);
-        o[0] = lo;
-        o[1] = hi;
+        // the next quad's staging writes bufA (last read by pass 3, barrier passed); its first pass writes bufB
+        // only after the barrier that follows the staging, i.e. after every thread finished this output loop
     }
 }
 
@@ -636,13 +656,25 @@ __global__ void k_bin_map(int W, int H, int Hp, int nr, int na, u16* __restrict_
 // ---- dispatch tables of the specialised shapes -------------------------------------------------
 template <int N, int R0, int R1, int R2, int R3>
 void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
+    constexpr int THREADS = ((2 * (N / 16) + 255) / 256) * 256;  // one 16-pixel staging task per thread
     const size_t smem = (size_t)(4 * N + 2 * (N / 16)) * sizeof(float2);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    k_rows_t<N, R0, R1, R2, R3><<<dim3(P.H / 4, nimg), kRowThreads, smem, st>>>(rgb, P, tw, specT);
+    // row quads per CTA: walks long enough to hide the first load, CTA counts that fill whole waves
+    const int per_sm = (int)((220 * 1024) / smem) > 0 ? (int)((220 * 1024) / smem) : 1;
+    const int nquads = P.H / 4, slots = per_sm * 148;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int qpc = 1; qpc <= 16 && qpc <= nquads; qpc++) {
+        const long long ctas = (long long)((nquads + qpc - 1) / qpc) * nimg;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (qpc + 0.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = qpc; }
+    }
+    k_rows_t<N, R0, R1, R2, R3, THREADS><<<dim3((nquads + best - 1) / best, nimg), THREADS, smem, st>>>(rgb, P, tw, specT, best);
 }
 
 template <int N, int R0, int R1, int R2, int R3, int NB>

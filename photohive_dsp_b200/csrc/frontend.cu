@@ -336,25 +336,26 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
                                                       const int* __restrict__ tie_list, const int* __restrict__ tie_n,
                                                       const u32* __restrict__ work, const u32* __restrict__ work_n,
                                                       u64* __restrict__ cells_tie) {
+    constexpr int MAXT = 64;  // tie groups of one image whose plans are cached in shared memory
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* tb_raw = smem_raw;
-    u16* gid_cache = reinterpret_cast<u16*>(smem_raw + phd_cell_tables_bytes());  // [chunk]
+    u16* tie_cache = reinterpret_cast<u16*>(smem_raw + phd_cell_tables_bytes());  // [chunk] tie index of each pixel
+    u16* tie_of_pair = tie_cache + P.chunk;                                       // [ncls*hp] (cls, hue bin) -> tie index
+    constexpr u16 NONE = 0xffff;
+    __shared__ GroupPlan tplan[MAXT];
     __shared__ int scan[256];
     __shared__ int sh_last;
     const int tid = threadIdx.x, T = P.T, NC = P.NC;
     const int ppt = P.chunk / 256;  // consecutive pixels per thread (16 or 32)
+    const int npairs = P.ncls * P.hp, spvp = P.sp * P.vp;
     const u32 n_items = *work_n;
     if (blockIdx.x >= n_items) return;
     phd_cell_tabs_to_smem(tb_raw, tabs_g);
-    __syncthreads();
     const unsigned char* svtab = tb_raw;
     const int qs = 20;  // tie cells are kept in Q20 like the global cells
     const CellCfg K = phd_cell_cfg(P, qs);
+    const bool fast_ok = P.ds <= 1 && P.aligned16 != 0;
 
-    auto pixel_at = [&](const uint8_t* base, long long i) -> PixOut {
-        const uint8_t* q = base + phd_src_index(i, P) * 3;
-        return phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc);
-    };
     auto accept = [&](u64* ct, const PixOut& o) {
         atomicAdd(ct + o.cell, 1ull);
         if (o.w0 >> 16) atomicAdd(ct + NC + o.cell, 1ull);
@@ -363,35 +364,67 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
         atomicAdd(ct + 4 * NC + o.cell, (u64)(o.hbits - PHD_MAGIC_RN_BITS) << (20 - qs));
     };
 
+    int cur_img = -1, nt = 0;
     for (u32 item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int img = (int)(work[item] / (u32)P.nchunks), chunk = (int)(work[item] % (u32)P.nchunks);
         const uint8_t* base = rgb + (size_t)img * P.image_stride;
-        const GroupPlan* plan = plan_g + (size_t)img * T;
         u64* ct = cells_tie + (size_t)img * PHD_CELL_Q * NC;
         const long long c0 = (long long)chunk * P.chunk;
-        __syncthreads();  // gid_cache of the previous item is no longer read
-        for (int i = 0; i < ppt; i++) {
-            const int li = tid * ppt + i;
-            int gid = 0xffff;
-            if (c0 + li < P.hpx) {
-                const PixOut o = pixel_at(base, c0 + li);
-                gid = phd_cell_group(o.cell, P);
-                const GroupPlan gp = plan[gid];
-                if (gp.mode == 2 && chunk < gp.cstar) accept(ct, o);  // whole chunk accepted
+        __syncthreads();  // the previous item's caches are no longer read
+        if (img != cur_img) {
+            // (cls, hue bin) -> index of its partly accepted tie group in this image's tie list
+            cur_img = img;
+            nt = tie_n[img];
+            for (int i = tid; i < npairs; i += 256) tie_of_pair[i] = NONE;
+            for (int k = tid; k < min(nt, MAXT); k += 256) tplan[k] = plan_g[(size_t)img * T + tie_list[(size_t)img * T + k]];
+            __syncthreads();
+            for (int k = 0; k < nt; k++) {
+                const int g = tie_list[(size_t)img * T + k];
+                if (g < P.hp * spvp) {
+                    if (tid == 0) { const int j = g / spvp, cls = g - j * spvp; tie_of_pair[cls * P.hp + j] = (u16)k; }
+                } else {
+                    const int cls = (g == T - 1) ? spvp + 1 : spvp;
+                    for (int j = tid; j < P.hp; j += 256) tie_of_pair[cls * P.hp + j] = (u16)k;
+                }
             }
-            gid_cache[li] = (u16)gid;
+            __syncthreads();
+        }
+        auto get_plan = [&](int k) -> GroupPlan {
+            return k < MAXT ? tplan[k] : plan_g[(size_t)img * T + tie_list[(size_t)img * T + k]];
+        };
+        // classify the chunk; pixels of tie groups whose accepted prefix covers the whole chunk are taken at once
+        const long long p0 = c0 + (long long)tid * ppt;
+        for (int i0 = 0; i0 < ppt; i0 += 16) {
+            u32 w[12];
+            const bool vec = fast_ok && p0 + i0 + 16 <= P.hpx;
+            if (vec) load48_aligned(base + (p0 + i0) * 3, w);
+#pragma unroll 4
+            for (int i = 0; i < 16; i++) {
+                const int li = tid * ppt + i0 + i;
+                u16 t = NONE;
+                if (c0 + li < P.hpx) {
+                    int R, G, B;
+                    if (vec) { R = packed_byte(w, 3 * i); G = packed_byte(w, 3 * i + 1); B = packed_byte(w, 3 * i + 2); }
+                    else {
+                        const uint8_t* q = base + phd_src_index(c0 + li, P) * 3;
+                        R = __ldg(q); G = __ldg(q + 1); B = __ldg(q + 2);
+                    }
+                    const PixOut o = phd_pixel(R, G, B, svtab, K, exc);
+                    t = tie_of_pair[o.cell >> 2];
+                    if (t != NONE && chunk < get_plan(t).cstar) accept(ct, o);  // whole chunk accepted
+                }
+                tie_cache[li] = t;
+            }
         }
         __syncthreads();
-        const int nt = tie_n[img];
         for (int k = 0; k < nt; k++) {
-            const int g = tie_list[(size_t)img * T + k];
-            const GroupPlan gp = plan[g];
-            const bool partial = (gp.mode == 2 && gp.cstar == chunk && gp.need > 0);
-            const bool last = (gp.mode == 2 && gp.clast == chunk);
+            const GroupPlan gp = get_plan(k);
+            const bool partial = (gp.cstar == chunk && gp.need > 0);
+            const bool last = (gp.clast == chunk);
             if (!partial && !last) continue;  // uniform across the block
             int mine = 0, my_last = -1;
             for (int i = 0; i < ppt; i++)
-                if (gid_cache[tid * ppt + i] == g) { mine++; my_last = tid * ppt + i; }
+                if (tie_cache[tid * ppt + i] == k) { mine++; my_last = tid * ppt + i; }
             scan[tid] = mine;
             if (tid == 0) sh_last = -1;
             __syncthreads();
@@ -405,10 +438,13 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
             const int last_idx = sh_last;
             for (int i = 0; i < ppt; i++) {
                 const int li = tid * ppt + i;
-                if (gid_cache[li] != g) continue;
+                if (tie_cache[li] != k) continue;
                 const bool take = (partial && rank < gp.need) || (last && li == last_idx);
                 rank++;
-                if (take) accept(ct, pixel_at(base, c0 + li));
+                if (take) {
+                    const uint8_t* q = base + phd_src_index(c0 + li, P) * 3;
+                    accept(ct, phd_pixel(__ldg(q), __ldg(q + 1), __ldg(q + 2), svtab, K, exc));
+                }
             }
             __syncthreads();
         }
@@ -561,7 +597,7 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
 
 void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                              const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
-    const size_t smem = phd_cell_tables_bytes() + (size_t)P.chunk * sizeof(u16);
+    const size_t smem = phd_cell_tables_bytes() + ((size_t)P.chunk + (size_t)P.ncls * P.hp) * sizeof(u16);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_palette_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -729,7 +729,7 @@ int phd_fft_plan_factors(int n, int* fac, int* nfac) {
 // Radix plans of the compile-time specialised lengths (must match the launch_*_t dispatch below).
 static bool special_radices(int n, int r[4]) {
     static const int tab[][5] = {{1920, 15, 8, 16, 1}, {3840, 15, 16, 16, 1}, {6000, 15, 25, 16, 1},
-                                 {1080, 15, 8, 9, 1},  {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1}};
+                                 {1080, 9, 10, 12, 1},  {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1}};
     for (const auto& t : tab)
         if (t[0] == n) { r[0] = t[1]; r[1] = t[2]; r[2] = t[3]; r[3] = t[4]; return true; }
     return false;
@@ -798,7 +798,7 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
     *launches += 1;
     if (P.Hp == P.H) {
         switch (P.H) {
-            case 1080: launch_cols_t<1080, 15, 8, 9, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 1080: launch_cols_t<1080, 9, 10, 12, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
         }

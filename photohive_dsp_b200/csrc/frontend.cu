@@ -221,24 +221,32 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
             ccp[P.T - 1] = (u16)gb[set ^ 1][1];
             gb[set ^ 1][0] = 0; gb[set ^ 1][1] = 0;
         }
+        // the four sub-cells of a (class, hue bin) pair are adjacent in every array: 16-byte accesses
         auto drain_pair = [&](int pair) -> u32 {
-            u32 cnt = 0;
-#pragma unroll
-            for (int sub = 0; sub < 4; sub++) {
-                const int cell = pair * 4 + sub;
-                const u32 v0 = cw[cell];
-                if (v0) {
-                    const u32 n = v0 & 0xffffu;
-                    cnt += n;
-                    acc_cnt[cell] += n;
-                    acc_n255[cell] += v0 >> 16;
-                    acc_mx[cell] += cw[ncs + cell];
-                    acc_s[cell] += cw[2 * ncs + cell] - n * PHD_MAGIC_RN_BITS;  // mod 2^32: the true sum fits
-                    acc_h[cell] += cw[3 * ncs + cell] - n * PHD_MAGIC_RN_BITS;
-                    cw[cell] = 0; cw[ncs + cell] = 0; cw[2 * ncs + cell] = 0; cw[3 * ncs + cell] = 0;
-                }
-            }
-            return cnt;
+            uint4* w0p = reinterpret_cast<uint4*>(cw) + pair;
+            const uint4 c = *w0p;
+            if ((c.x | c.y | c.z | c.w) == 0) return 0;
+            uint4* w1p = reinterpret_cast<uint4*>(cw + ncs) + pair;
+            uint4* w2p = reinterpret_cast<uint4*>(cw + 2 * ncs) + pair;
+            uint4* w3p = reinterpret_cast<uint4*>(cw + 3 * ncs) + pair;
+            const uint4 m = *w1p, sv = *w2p, hv = *w3p;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            *w0p = z; *w1p = z; *w2p = z; *w3p = z;
+            const uint4 n = make_uint4(c.x & 0xffffu, c.y & 0xffffu, c.z & 0xffffu, c.w & 0xffffu);
+            uint4* ac = reinterpret_cast<uint4*>(acc_cnt) + pair;
+            uint4* an = reinterpret_cast<uint4*>(acc_n255) + pair;
+            uint4* am = reinterpret_cast<uint4*>(acc_mx) + pair;
+            uint4 t = *ac; t.x += n.x; t.y += n.y; t.z += n.z; t.w += n.w; *ac = t;
+            t = *an; t.x += c.x >> 16; t.y += c.y >> 16; t.z += c.z >> 16; t.w += c.w >> 16; *an = t;
+            t = *am; t.x += m.x; t.y += m.y; t.z += m.z; t.w += m.w; *am = t;
+            // sums carry count * bias (mod 2^32): the true chunk sums fit 32 bits
+            ulonglong2* as = reinterpret_cast<ulonglong2*>(acc_s) + 2 * pair;
+            ulonglong2* ah = reinterpret_cast<ulonglong2*>(acc_h) + 2 * pair;
+            ulonglong2 u = as[0]; u.x += sv.x - n.x * PHD_MAGIC_RN_BITS; u.y += sv.y - n.y * PHD_MAGIC_RN_BITS; as[0] = u;
+            u = as[1]; u.x += sv.z - n.z * PHD_MAGIC_RN_BITS; u.y += sv.w - n.w * PHD_MAGIC_RN_BITS; as[1] = u;
+            u = ah[0]; u.x += hv.x - n.x * PHD_MAGIC_RN_BITS; u.y += hv.y - n.y * PHD_MAGIC_RN_BITS; ah[0] = u;
+            u = ah[1]; u.x += hv.z - n.z * PHD_MAGIC_RN_BITS; u.y += hv.w - n.w * PHD_MAGIC_RN_BITS; ah[1] = u;
+            return n.x + n.y + n.z + n.w;
         };
         for (int pair = tid; pair < npairs_colour; pair += THREADS) {
             const int cls = pair / hp, j = pair - cls * hp;

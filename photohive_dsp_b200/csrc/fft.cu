@@ -32,6 +32,9 @@ namespace {
 
 #define PHD_GRAY_BIAS 127500
 constexpr int kRowThreads = 256;
+#ifndef PHD_ROWS_PAIRS_1920
+#define PHD_ROWS_PAIRS_1920 2
+#endif
 constexpr int kColThreads = 512;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
@@ -294,42 +297,42 @@ __device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Rows, specialised: one CTA transforms four image rows (two packed complex sequences) and writes, for every
-// spectrum column x, the four consecutive entries specT[x][4j..4j+3] as one 32-byte sector.
-// Requires W % 16 == 0, H % 4 == 0, 16-byte aligned rows.
+// Rows, specialised: one CTA transforms PAIRS row pairs at a time (each pair = one packed complex sequence) and
+// writes, for every spectrum column x, the 2*PAIRS consecutive entries specT[x][2*PAIRS*j ..] (32-byte sectors
+// with PAIRS = 2.  PAIRS = 1 writes 16-byte half sectors: measured 1.9x SLOWER on 3840- and 6000-pixel rows
+// despite three times the resident CTAs -- partial-sector writes are that expensive -- so every shape uses 2).
+// Requires W % 16 == 0, H % (2*PAIRS) == 0, 16-byte aligned rows.
 // ------------------------------------------------------------------------------------------
-template <int N, int R0, int R1, int R2, int R3, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
-                                                        const float2* __restrict__ twp, float2* __restrict__ specT,
-                                                        int qpc) {
+template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
+__global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 * 1024) ? 3 : ((PAIRS * (2 * N + N / 16) * 8 <= 110 * 1024) ? 2 : 1)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
+                                                    const float2* __restrict__ twp, float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = N + N / 16;  // padded length
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [2][NP]  (also pass scratch: [2][N] fits)
-    float2* bufB = bufA + 2 * NP;                        // [2][N]
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [PAIRS][NP]  (also pass scratch: [PAIRS][N] fits)
+    float2* bufB = bufA + PAIRS * NP;                    // [PAIRS][N]
     const int img = blockIdx.y;
-    const int nquads = P.H / 4;
-    // quads blockIdx.x, blockIdx.x + gridDim.x, ...: CTAs that run together work on neighbouring rows, so the
-    // 32-byte sectors they write into the same 128-byte lines of the transposed spectrum meet in L2
-    const int q_begin = blockIdx.x, q_end = nquads, q_step = gridDim.x;
-    (void)qpc;
+    const int nsteps = P.H / (2 * PAIRS);
+    // steps blockIdx.x, blockIdx.x + gridDim.x, ...: CTAs that run together work on neighbouring rows, so the
+    // pieces they write into the same 128-byte lines of the transposed spectrum meet in L2
+    const int q_begin = blockIdx.x, q_end = nsteps, q_step = gridDim.x;
     const uint8_t* img_base = rgb + (size_t)img * P.image_stride;
-    // A CTA walks qpc consecutive row quads.  Per quad: 2 row pairs x N/16 segments of 16 pixels; one task (thread)
-    // holds the segment of BOTH rows of its pair (2 x three 16-byte loads).  The loads of quad q+1 are issued
-    // before the passes of quad q and stay in registers meanwhile.
+    // Per step: PAIRS row pairs x N/16 segments of 16 pixels; one task (thread) holds the segment of BOTH rows of
+    // its pair (2 x three 16-byte loads).  The loads of the next step are issued before the passes of this one and
+    // stay in registers meanwhile.
     constexpr int SEGS = N / 16;
-    static_assert(2 * SEGS <= THREADS, "one staging task per thread");
+    static_assert(PAIRS * SEGS <= THREADS, "one staging task per thread");
     const int task = threadIdx.x;
-    const bool has_task = task < 2 * SEGS;
+    const bool has_task = task < PAIRS * SEGS;
     const int pair = task / SEGS, seg = task - pair * SEGS;
     uint4 a0, b0, c0, a1, b1, c1;
-    auto load_quad = [&](int q) {
-        const uint8_t* base = img_base + (size_t)(4 * q) * N * 3;
+    auto load_step = [&](int q) {
+        const uint8_t* base = img_base + (size_t)(2 * PAIRS * q) * N * 3;
         const uint4* s0 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair) * N * 3 + (size_t)seg * 48);
         const uint4* s1 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair + 1) * N * 3 + (size_t)seg * 48);
         a0 = __ldg(s0); b0 = __ldg(s0 + 1); c0 = __ldg(s0 + 2);
         a1 = __ldg(s1); b1 = __ldg(s1 + 1); c1 = __ldg(s1 + 2);
     };
-    if (has_task && q_begin < q_end) load_quad(q_begin);
+    if (has_task && q_begin < q_end) load_step(q_begin);
     const int fw = N / 2 + 1;
     for (int q = q_begin; q < q_end; q += q_step) {
         if (has_task) {
@@ -347,27 +350,21 @@ __global__ void __launch_bounds__(THREADS) k_rows_t(const uint8_t* __restrict__ 
                                114 * (int)__byte_perm(w1[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
                 dst[i] = make_float2((float)g0, (float)g1);
             }
-            if (q + q_step < q_end) load_quad(q + q_step);
+            if (q + q_step < q_end) load_step(q + q_step);
         }
         __syncthreads();
-        const float2* z = fft_run_t<N, R0, R1, R2, R3, true>(bufA, bufB, twp, 2, NP, N);
-        float2* out = specT + (size_t)img * fw * P.Hp + 4 * q;
+        const float2* z = fft_run_t<N, R0, R1, R2, R3, true>(bufA, bufB, twp, PAIRS, NP, N);
+        float2* out = specT + (size_t)img * fw * P.Hp + 2 * PAIRS * q;
         for (int k = threadIdx.x; k < fw; k += blockDim.x) {
             const int kc = k == 0 ? 0 : N - k;
-            float4 lo, hi;
-            {
-                const float2 zk = z[k], zc = z[kc];
-                lo = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-            }
-            {
-                const float2 zk = z[N + k], zc = z[N + kc];
-                hi = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-            }
             float4* o = reinterpret_cast<float4*>(out + (size_t)k * P.Hp);
-            o[0] = lo;
-            o[1] = hi;
+#pragma unroll
+            for (int pr = 0; pr < PAIRS; pr++) {
+                const float2 zk = z[pr * N + k], zc = z[pr * N + kc];
+                o[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            }
         }
-        // the next quad's staging writes bufA (last read by pass 3, barrier passed); its first pass writes bufB
+        // the next step's staging writes bufA (last read by pass 3, barrier passed); its first pass writes bufB
         // only after the barrier that follows the staging, i.e. after every thread finished this output loop
     }
 }
@@ -654,27 +651,25 @@ __global__ void k_bin_map(int W, int H, int Hp, int nr, int na, u16* __restrict_
 }
 
 // ---- dispatch tables of the specialised shapes -------------------------------------------------
-template <int N, int R0, int R1, int R2, int R3>
+template <int N, int R0, int R1, int R2, int R3, int PAIRS>
 void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
-    constexpr int THREADS = ((2 * (N / 16) + 255) / 256) * 256;  // one 16-pixel staging task per thread
-    const size_t smem = (size_t)(4 * N + 2 * (N / 16)) * sizeof(float2);
+    constexpr int THREADS = ((PAIRS * (N / 16) + 127) / 128) * 128;  // one 16-pixel staging task per thread
+    const size_t smem = (size_t)PAIRS * (2 * N + N / 16) * sizeof(float2);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    // row quads per CTA: walks long enough to hide the first load, CTA counts that fill whole waves
-    const int per_sm = (int)((220 * 1024) / smem) > 0 ? (int)((220 * 1024) / smem) : 1;
-    const int nquads = P.H / 4, slots = per_sm * 148;
-    int best = 1;
-    double best_cost = 1e30;
-    for (int qpc = 1; qpc <= 16 && qpc <= nquads; qpc++) {
-        const long long ctas = (long long)((nquads + qpc - 1) / qpc) * nimg;
-        const long long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * (qpc + 0.5);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = qpc; }
-    }
-    k_rows_t<N, R0, R1, R2, R3, THREADS><<<dim3((nquads + best - 1) / best, nimg), THREADS, smem, st>>>(rgb, P, tw, specT, best);
+    // CTAs walk strided steps; about four resident waves keep the tail short
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
+    if (per_sm < 1) per_sm = 1;
+    const int nsteps = P.H / (2 * PAIRS);
+    long long want = (long long)per_sm * 148 * 4;
+    int gx = (int)((want + nimg - 1) / nimg);
+    if (gx > nsteps) gx = nsteps;
+    if (gx < 1) gx = 1;
+    k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS><<<dim3(gx, nimg), THREADS, smem, st>>>(rgb, P, tw, specT);
 }
 
 template <int N, int R0, int R1, int R2, int R3, int NB>
@@ -768,9 +763,9 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
     *launches += 1;
     if (rows_fast_ok(P)) {
         switch (P.W) {
-            case 1920: launch_rows_t<1920, 15, 8, 16, 1>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 3840: launch_rows_t<3840, 15, 16, 16, 1>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 6000: launch_rows_t<6000, 15, 25, 16, 1>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 1920: launch_rows_t<1920, 15, 8, 16, 1, PHD_ROWS_PAIRS_1920>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 3840: launch_rows_t<3840, 15, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 6000: launch_rows_t<6000, 15, 25, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
         }
     }
     const size_t smem = (size_t)P.W * 2 * sizeof(float2);

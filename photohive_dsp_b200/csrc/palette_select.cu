@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     int* keep = take + T;                            // [T] tie groups: last pixel survives
     int* scnt = keep + T;                            // [T] per parent slot: pixels that end up in it
     u32* cbits = reinterpret_cast<u32*>(scnt + T);   // [(nchunks+31)/32] chunks the tie path must revisit
-    __shared__ int sh_N, sh_nt;
+    int* scan_list = nmin;                           // [T] partly accepted tie groups (nmin[] is dead by then)
+    __shared__ int sh_N, sh_nt, sh_nscan;
     __shared__ u64 sh_ssum;
 
     const double* gh = centres;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     // pixel count of every group, and the image's saturation sum, from the cells
     for (int g = tid; g < T; g += blockDim.x) n[g] = 0;
     for (int w = tid; w < nbw; w += blockDim.x) cbits[w] = 0;
-    if (tid == 0) sh_ssum = 0;
+    if (tid == 0) { sh_ssum = 0; sh_nscan = 0; }
     __syncthreads();
     {
         u64 ssum = 0;
@@ -241,31 +242,8 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
             gp.slot = (short)first[g];
             if (take[g] < 0 || take[g] >= n[g]) gp.mode = 1;  // sole nearest parent, or a tie whose pixels all fit
             else {
-                gp.mode = 2;
-                const u16* cc = counts_chunk + (size_t)img * P.nchunks * T + g;
-                const int tk = take[g];
-                int cum = 0, cstar = -1, need = 0, clast = -1;
-                bool found = (tk == 0);
-                for (int c = 0; c < P.nchunks; c++) {
-                    const int k = cc[(size_t)c * T];
-                    if (k == 0) continue;
-                    clast = c;
-                    if (!found) {
-                        atomicOr(&cbits[c >> 5], 1u << (c & 31));
-                        if (cum + k >= tk) { cstar = c; need = tk - cum; found = true; }
-                        cum += k;
-                    }
-                }
-                gp.cstar = cstar;
-                gp.need = need;
-                gp.clast = keep[g] ? clast : -1;
-                if (gp.clast >= 0) atomicOr(&cbits[gp.clast >> 5], 1u << (gp.clast & 31));
-                // its tie cells start from zero
-                u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
-                int c0, nc;
-                phd_group_cell_range(P, g, &c0, &nc);
-                for (int q = 0; q < PHD_CELL_Q; q++)
-                    for (int c = 0; c < nc; c++) ct[(size_t)q * P.NC + c0 + c] = 0;
+                gp.mode = 2;  // c*, need and clast are filled in by the warp scan below
+                scan_list[atomicAdd(&sh_nscan, 1)] = g;
             }
         }
         plan_g[(size_t)img * T + g] = gp;
@@ -282,6 +260,57 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     for (int j = tid; j < T; j += blockDim.x) {
         parent_ids[(size_t)img * T + j] = j < N ? ids[j] : -1;
         if (j < N) atomicAdd(&sacc[(size_t)img * T + j].cnt, (u64)scnt[j]);
+    }
+    __syncthreads();
+    // one WARP per partly accepted tie group walks the per-chunk counts (32 chunks per step): the chunk c* where the
+    // accepted prefix ends, how many of its pixels are still accepted, the chunk of the group's last pixel, and the
+    // chunks the tie kernel has to revisit
+    {
+        const int lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+        for (int e = wid; e < sh_nscan; e += nwarps) {
+            const int g = scan_list[e];
+            const u16* cc = counts_chunk + (size_t)img * P.nchunks * T + g;
+            const int tk = take[g];
+            int cum = 0, cstar = -1, need = 0, clast = -1;
+            bool found = (tk == 0);
+            for (int base = 0; base < P.nchunks; base += 32) {
+                const int c = base + lane;
+                const int k = c < P.nchunks ? (int)cc[(size_t)c * T] : 0;
+                int incl = k;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const unsigned nz = __ballot_sync(0xffffffffu, k > 0);
+                if (nz) clast = base + 31 - __clz(nz);
+                if (!found) {
+                    const int before = cum + incl - k;
+                    if (k > 0 && before < tk) atomicOr(&cbits[c >> 5], 1u << (c & 31));
+                    const unsigned hit = __ballot_sync(0xffffffffu, k > 0 && cum + incl >= tk);
+                    if (hit) {
+                        const int L = __ffs(hit) - 1;
+                        cstar = base + L;
+                        need = tk - __shfl_sync(0xffffffffu, before, L);
+                        found = true;
+                    }
+                    cum += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+            if (!keep[g]) clast = -1;
+            if (lane == 0) {
+                GroupPlan* gp = plan_g + (size_t)img * T + g;
+                gp->cstar = cstar;
+                gp->need = need;
+                gp->clast = clast;
+                if (clast >= 0) atomicOr(&cbits[clast >> 5], 1u << (clast & 31));
+            }
+            // its tie cells start from zero
+            u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
+            int c0, nc;
+            phd_group_cell_range(P, g, &c0, &nc);
+            for (int i = lane; i < PHD_CELL_Q * nc; i += 32) ct[(size_t)(i / nc) * P.NC + c0 + (i % nc)] = 0;
+        }
     }
     __syncthreads();
     for (int w = tid; w < nbw; w += blockDim.x) {

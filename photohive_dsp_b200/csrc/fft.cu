@@ -357,11 +357,22 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
         float2* out = specT + (size_t)img * fw * P.Hp + 2 * PAIRS * q;
         for (int k = threadIdx.x; k < fw; k += blockDim.x) {
             const int kc = k == 0 ? 0 : N - k;
-            float4* o = reinterpret_cast<float4*>(out + (size_t)k * P.Hp);
+            float4 v[PAIRS];
 #pragma unroll
             for (int pr = 0; pr < PAIRS; pr++) {
                 const float2 zk = z[pr * N + k], zc = z[pr * N + kc];
-                o[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+                v[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            }
+            float* o = reinterpret_cast<float*>(out + (size_t)k * P.Hp);
+            if (PAIRS == 2) {
+                // one 32-byte store = one full sector per thread (sm_100 256-bit vector store)
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(v[0].x), "f"(v[0].y),
+                             "f"(v[0].z), "f"(v[0].w), "f"(v[PAIRS - 1].x), "f"(v[PAIRS - 1].y), "f"(v[PAIRS - 1].z),
+                             "f"(v[PAIRS - 1].w)
+                             : "memory");
+            } else {
+#pragma unroll
+                for (int pr = 0; pr < PAIRS; pr++) reinterpret_cast<float4*>(o)[pr] = v[pr];
             }
         }
         // the next step's staging writes bufA (last read by pass 3, barrier passed); its first pass writes bufB

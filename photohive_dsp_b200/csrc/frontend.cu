@@ -150,6 +150,11 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     const unsigned char* svtab = tb_raw;
     const CellCfg K = phd_cell_cfg(P, QS);
     const int spvp = P.sp * P.vp, hp = P.hp, npairs_colour = spvp * hp;
+    {   // keep the table pointer in registers: the compiler would reload it from the constant bank per pixel
+        unsigned long long e;
+        asm volatile("mov.u64 %0, %1;" : "=l"(e) : "l"(exc));
+        exc = reinterpret_cast<const unsigned char*>(e);
+    }
     const u32 cw_base0 = (u32)__cvta_generic_to_shared(chunkW);
     const u32 stride_b = 4u * (u32)ncs;
     const u32 set_b = 4u * stride_b;  // bytes between the two chunk sets
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, unsigned
 }
 
 // Exceptional-colour codes (pixel_cells.cuh): for every colour whose hue is exactly k * Lh/2, what the reference's
-// doubles make of it.  code = ((cell delta + 4) << 1) | full, relative to the ordinary cell cls*4hp + 2k + 1.
+// doubles make of it.  code = full << 7 | (cell delta + 4), relative to the ordinary cell cls*4hp + 2k + 1.
 __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* __restrict__ out, int* __restrict__ ok) {
     __shared__ double k255[256];
     phd_fill_k255(k255);
@@ -554,7 +559,7 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
                 delta = below ? -2 : 0;  // (j, end of the lower half) | (j, upper half)
                 full = below ? 1 : 0;
             }
-            code = (delta + 4) * 2 + full;
+            code = (full << 7) | (delta + 4);
         }
     }
     out[c] = (unsigned char)code;

@@ -49,7 +49,7 @@ struct CellCfg {
     float eps;      // guard of the half-bin floor
     float qscale;   // 2^QS
     u32 sat1_bits;  // bits of MAGIC + round(0.999999 * 2^QS)
-    u32 full_bits;  // bits of MAGIC + (2^QS - 1): an edge pixel that counts as the END of its half bin
+    u32 full_val;   // 2^QS - 1: hue fraction of an edge pixel that counts as the END of its half bin
 };
 
 #define PHD_MAGIC_RN 12582912.0f   // 1.5 * 2^23: x + MAGIC has round(x) in its low mantissa bits (|x| < 2^22)
@@ -68,7 +68,7 @@ __device__ __forceinline__ CellCfg phd_cell_cfg(const DevParams& P, int qs) {
     c.eps = phd_cell_eps(P.hp);
     c.qscale = (float)(1u << qs);
     c.sat1_bits = PHD_MAGIC_RN_BITS + (u32)__double2uint_rn(0.999999 * (double)(1u << qs));
-    c.full_bits = PHD_MAGIC_RN_BITS + ((1u << qs) - 1u);
+    c.full_val = (1u << qs) - 1u;
     return c;
 }
 
@@ -112,10 +112,12 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
     // cell = cls*4hp + 2*halfbin + 1, i.e. (cls*hp + (hb>>1))*4 + (hb odd ? 3 : 1)
     int cell = cls * K.hp4 + (int)(2u * __float_as_uint(hbm) + (1u - 2u * PHD_MAGIC_FLOOR_BITS));
     if (rem == 0.0f && q != 0) {
-        // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc)
-        const u32 code = __ldg(exc + ((u32)R | ((u32)G << 8) | ((u32)B << 16)));
-        cell += (int)(code >> 1) - 4;
-        hbits = (code & 1u) ? K.full_bits : PHD_MAGIC_RN_BITS;
+        // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc);
+        // code = full << 7 | (cell delta + 4)
+        const u32 idx = __byte_perm(__byte_perm((u32)R, (u32)G, 0x1140), (u32)B, 0x3410);  // R | G << 8 | B << 16
+        const u32 code = __ldg(exc + idx);
+        cell += (int)(code & 0x7fu) - 4;
+        hbits = PHD_MAGIC_RN_BITS + (code >> 7) * K.full_val;
     }
     // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
     u32 sbits = __float_as_uint(fmaf(qf * phd_rcp((float)mx), K.qscale, PHD_MAGIC_RN));

@@ -91,6 +91,42 @@ def test_report_matches_oracle(ctx, oracle, W, H, kind, kw):
     assert got.extra["dropped_pixels"] == want.extra["dropped_pixels"]
 
 
+def _exceptional_colour_image(hp, W, H, seed, gray_fraction):
+    """Pixels whose hue sits EXACTLY on a half-hue-bin boundary (where the reference's double rounding decides the bin
+    and the side of the wrap seam), plus a gray area so that a gray / black parent (seam at 180 degrees) is selected."""
+    c = np.arange(1 << 24, dtype=np.int64)
+    R, G, B = c & 255, (c >> 8) & 255, c >> 16
+    mx, mn = np.maximum(R, np.maximum(G, B)), np.minimum(R, np.minimum(G, B))
+    q = mx - mn
+    is_r = R == mx
+    is_g = (~is_r) & (G == mx)
+    p = np.where(is_r, G - B, np.where(is_g, B - R, R - G))
+    num2 = 120 * (np.where(is_r, 0, np.where(is_g, 2, 4)) * q + p)
+    num2 = np.where(num2 < 0, num2 + 720 * q, num2)
+    exc = c[(q > 0) & (num2 % np.maximum((360 // hp) * q, 1) == 0)]
+    rng = np.random.default_rng(seed)
+    pick = exc[rng.integers(0, len(exc), W * H)]
+    img = np.stack([pick & 255, (pick >> 8) & 255, pick >> 16], -1).astype(np.uint8).reshape(H, W, 3)
+    n_gray = int(H * gray_fraction)
+    img[:n_gray] = rng.integers(40, 200, (n_gray, W, 1)).astype(np.uint8)  # R == G == B: saturation 0
+    return img
+
+
+@pytest.mark.parametrize("hp,cov,frac", [(18, 0.5, 0.3), (18, 0.95, 0.0), (9, 0.4, 0.3), (36, 0.3, 0.5), (12, 0.7, 0.1)])
+def test_boundary_colours_follow_the_reference_rounding(ctx, oracle, hp, cov, frac):
+    """Every coloured pixel is an 'exceptional' one (pixel_cells.cuh): exact on a half-bin boundary.  Few parents are
+    selected, so far-away groups join them and their pixels cross the wrap seams of calculate_avg_hsv."""
+    kw = dict(h_partitions=hp, coverage_thresh=cov)
+    img = _exceptional_colour_image(hp, 640, 480, 77 + hp, frac)
+    want = oracle.report(img, omake(**kw), nthreads=8)
+    got = report_from_batch(ctx.get_reports(img[None], params=make_params(**kw)), 0)
+    assert_report_close(got, want, f"exceptional colours hp={hp}")
+    assert np.array_equal(got.extra["parent_ids"], want.extra["parent_ids"])
+    assert got.extra["dropped_pixels"] == want.extra["dropped_pixels"]
+    counts = ctx.debug_group_counts(img, make_params(**kw))
+    assert np.array_equal(counts, oracle.report(img, omake(**kw), stages=1).extra["group_counts"])
+
+
 def test_batch_is_deterministic_and_position_independent(ctx, oracle):
     """Integer accumulators: a record does not depend on where the image sits in a batch, nor on the run."""
     imgs = np.stack([oracle.generate(k % 3, 50 + k, 640, 480) for k in range(7)])

@@ -144,20 +144,38 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
         __syncthreads();
     }
 
-    if (tid == 0) {
-        if (!safe) {
-            // insertion sort exactly as custom_sort walks it
-            for (int i = 1; i < T; i++) {
-                for (int j = i; j > 0; j--) {
-                    const int a = ids[j], b = ids[j - 1];
-                    if (trunc_f2i_x86(__fsub_rn(sal[b], sal[a])) < 0) {
-                        ids[j] = b;
-                        ids[j - 1] = a;
-                    } else
-                        break;
-                }
+    if (!safe && tid < 32) {
+        // insertion sort exactly as custom_sort walks it (utilities.c:132-153), one element at a time, but the walk of
+        // an element is done 32 positions per step by a warp: the element passes predecessor p while
+        // (int)(sal[p] - sal[x]) < 0 and stops at the FIRST predecessor (from the right) that does not let it pass.
+        const int lane = tid;
+        for (int i = 1; i < T; i++) {
+            const int x = ids[i];
+            const float v = sal[x];
+            int pos = 0;
+            for (int hi = i; hi > 0; hi -= 32) {
+                const int j = hi - 1 - lane;  // lane 0 looks at the nearest predecessor
+                bool blocks = false;
+                if (j >= 0) blocks = !(trunc_f2i_x86(__fsub_rn(sal[ids[j]], v)) < 0);
+                const unsigned m = __ballot_sync(0xffffffffu, blocks);
+                if (m) { pos = hi - (__ffs(m) - 1); break; }
             }
+            if (pos < i) {  // shift ids[pos .. i-1] one to the right, from the right end, then drop x into the gap
+                for (int hi = i; hi > pos; hi -= 32) {
+                    const int j = hi - 1 - lane;
+                    int val = 0;
+                    if (j >= pos) val = ids[j];
+                    __syncwarp();
+                    if (j >= pos) ids[j + 1] = val;
+                    __syncwarp();
+                }
+                if (lane == 0) ids[pos] = x;
+            }
+            __syncwarp();
         }
+    }
+    __syncthreads();
+    if (tid == 0) {
         int goal = (int)((double)P.hpx * P.coverage);
         int N = 0;
         for (int i = 0; i < T; i++) {

@@ -296,6 +296,18 @@ __device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
     return 299 * (int)__ldg(p) + 587 * (int)__ldg(p + 1) + 114 * (int)__ldg(p + 2);
 }
 
+// Gray numerator 299 R + 587 G + 114 B - 127500 of pixel i (0..15) of 48 packed bytes: two 2-way dot products
+// (16-bit weights x bytes, IDP.2A) straight on the packed words, whatever the pixel's byte alignment.
+__device__ __forceinline__ int gray16(const u32 (&w)[12], int i) {
+    const int b = 3 * i, k = b >> 2, s = b & 3;
+    const u32 bias = (u32)(-PHD_GRAY_BIAS);
+    constexpr u32 RG = 299u | (587u << 16), B_ = 114u, _R = 299u << 16, GB = 587u | (114u << 16);
+    if (s == 0) return (int)__dp2a_hi(B_, w[k], __dp2a_lo(RG, w[k], bias));       // R G B .
+    if (s == 1) return (int)__dp2a_hi(GB, w[k], __dp2a_lo(_R, w[k], bias));       // . R G B
+    if (s == 2) return (int)__dp2a_lo(B_, w[k + 1], __dp2a_hi(RG, w[k], bias));   // . . R G | B
+    return (int)__dp2a_lo(GB, w[k + 1], __dp2a_hi(_R, w[k], bias));               // . . . R | G B
+}
+
 // ------------------------------------------------------------------------------------------
 // Rows, specialised: one CTA transforms PAIRS row pairs at a time (each pair = one packed complex sequence) and
 // writes, for every spectrum column x, the 2*PAIRS consecutive entries specT[x][2*PAIRS*j ..] (32-byte sectors
@@ -340,16 +352,7 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
             const u32 w1[12] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, c1.z, c1.w};
             float2* dst = bufA + pair * NP + seg * 17;
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int bR = 3 * i, bG = 3 * i + 1, bB = 3 * i + 2;
-                const int g0 = 299 * (int)__byte_perm(w0[bR >> 2], 0u, 0x4440u + (bR & 3)) +
-                               587 * (int)__byte_perm(w0[bG >> 2], 0u, 0x4440u + (bG & 3)) +
-                               114 * (int)__byte_perm(w0[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
-                const int g1 = 299 * (int)__byte_perm(w1[bR >> 2], 0u, 0x4440u + (bR & 3)) +
-                               587 * (int)__byte_perm(w1[bG >> 2], 0u, 0x4440u + (bG & 3)) +
-                               114 * (int)__byte_perm(w1[bB >> 2], 0u, 0x4440u + (bB & 3)) - PHD_GRAY_BIAS;
-                dst[i] = make_float2((float)g0, (float)g1);
-            }
+            for (int i = 0; i < 16; i++) dst[i] = make_float2((float)gray16(w0, i), (float)gray16(w1, i));
             if (q + q_step < q_end) load_step(q + q_step);
         }
         __syncthreads();
@@ -478,7 +481,8 @@ __device__ __forceinline__ float cols_accumulate(int H, int ncol, const float2* 
                 const float raw = fmaf(v.x, v.x, v.y * v.y);
                 mymax = fmaxf(mymax, raw);
                 if (raw >= thr) {
-                    const u32 q = (u32)__float2int_rn((__log2f(raw) + lg2c) * kq);
+                    // clamped at 0: log2(raw) + lg2c can round a hair below 0 when p == 1
+                    const u32 q = (u32)__float2int_rn(fmaxf((__log2f(raw) + lg2c) * kq, 0.f));
                     const int bin = mp[i];
                     if (bin != run_bin) {
                         if (run_sum) {

@@ -70,6 +70,53 @@ class BatchReports:
     def __len__(self):
         return self.raw.shape[0]
 
+    # ---- export: the reference's Report.to_json() schema (core.py:388-436), for a whole batch --------------
+    def palette_rgb(self) -> np.ndarray:
+        """[n, T, 3] integer RGB of every palette entry, vectorised twin of utils.hsv_to_rgb (utils.py:8-28)."""
+        h, s, v = self.palette_hsv[..., 0], self.palette_hsv[..., 1], self.palette_hsv[..., 2]
+        chroma = v * s
+        second = chroma * (1 - np.abs((h / 60) % 2 - 1))
+        base = v - chroma
+        sector = np.minimum((h // 60).astype(np.int64), 5)
+        zero = np.zeros_like(chroma)
+        r = np.choose(sector, [chroma, second, zero, zero, second, chroma])
+        g = np.choose(sector, [second, chroma, chroma, second, zero, zero])
+        b = np.choose(sector, [zero, zero, second, chroma, chroma, second])
+        with np.errstate(invalid="ignore"):
+            return np.stack([((r + base) * 255), ((g + base) * 255), ((b + base) * 255)], -1).astype(np.int64)
+
+    def to_dicts(self, height: int, width: int) -> list[dict]:
+        """One dict per record with exactly the keys (and key order) of the reference's Report.to_json()."""
+        rgb = self.palette_rgb()
+        out = []
+        names = ("Red Brightness", "Green Brightness", "Blue Brightness", "Red Contrast", "Green Contrast", "Blue Contrast")
+        for i in range(len(self)):
+            d = {"Height": int(height), "Width": int(width), "Average Saturation": float(self.average_saturation[i])}
+            d.update({k: float(x) for k, x in zip(names, self.rgb_stats[i])})
+            for k in range(10):
+                d[f"Blur Vector {k+1} Angle"] = int(self.blur_vec_angle[i, k])
+                d[f"Blur Vector {k+1} Magnitude"] = float(self.blur_vec_mag[i, k])
+            n = int(self.palette_n[i])
+            for k in range(100):
+                if k < n:
+                    c = rgb[i, k]
+                    d[f"Color {k+1} H"], d[f"Color {k+1} S"], d[f"Color {k+1} V"] = int(c[0]), int(c[1]), int(c[2])
+                    d[f"Color {k+1} Percentage"] = float(self.palette_pct[i, k])
+                else:
+                    d[f"Color {k+1} H"] = d[f"Color {k+1} S"] = d[f"Color {k+1} V"] = 0
+                    d[f"Color {k+1} Percentage"] = 0
+            ns = 0 if self.sharpness is None else self.sharpness.shape[1]
+            for k in range(10):
+                d[f"Sharpness {k+1}:"] = float(self.sharpness[i, k]) if k < ns else 0.0
+            out.append(d)
+        return out
+
+    def to_json(self, i: int, height: int, width: int) -> str:
+        """JSON text of record i, formatted like the reference's Report.to_json()."""
+        import json
+        one = BatchReports(**{k: (v[i:i + 1] if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items()})
+        return json.dumps(one.to_dicts(height, width)[0], indent=4)
+
 
 def view_records(raw: np.ndarray, lay: phd_flat_layout) -> BatchReports:
     n = raw.shape[0]

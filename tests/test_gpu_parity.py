@@ -205,6 +205,21 @@ def test_python_get_report_surface(oracle):
     assert P.get_report(np.zeros((349, 350, 3), np.uint8)) is None
 
 
+def test_batch_json_export_equals_single_report_json(ctx, oracle):
+    """BatchReports.to_json / to_dicts carry the reference's to_json() schema (core.py:388-436) for a whole batch."""
+    import json
+    import photohive_dsp_b200 as P
+    imgs = np.stack([oracle.generate(k % 3, 300 + k, 640, 480) for k in range(3)])
+    boxes = [dict(top=0, bottom=240, left=0, right=320), dict(top=100, bottom=480, left=300, right=640)]
+    barr = np.array([[[b["top"], b["bottom"], b["left"], b["right"]] for b in boxes]] * 3, np.int32)
+    batch = ctx.get_reports(imgs, boxes=barr)
+    dicts = batch.to_dicts(480, 640)
+    for i in range(3):
+        single = json.loads(P.get_report(imgs[i], salient_characters=P.set_bounding_boxes(boxes)).to_json())
+        assert list(single.keys()) == list(dicts[i].keys())
+        assert single == dicts[i] == json.loads(batch.to_json(i, 480, 640))
+
+
 def test_non_8bit_image_is_refused_loudly(capfd):
     from oracle import binding
     from photohive_dsp_b200 import lib as L

@@ -22,7 +22,8 @@
 //
 // The *_t kernels are compile-time specialised (length and radix plan as template arguments: radix-15/16/25...
 // register butterflies with folded constants) for the shapes of BASELINE.json; every other size whose prime
-// factors are <= 31 runs the *_generic kernels (runtime radix list 4/2/3/5/p).
+// factors are <= 1021 runs the *_generic kernels (runtime radix list 4/2/3/5 and an O(p^2) butterfly for other primes p:
+// slow for large p, but camera sizes such as 6016x4016 = (2^7*47) x (2^4*251) are served rather than refused).
 #include <math.h>
 
 #include "fft_tables.cuh"
@@ -31,6 +32,7 @@
 namespace {
 
 #define PHD_GRAY_BIAS 127500
+#define PHD_MAX_PRIME 1021
 constexpr int kRowThreads = 256;
 #ifndef PHD_ROWS_PAIRS_1920
 #define PHD_ROWS_PAIRS_1920 2
@@ -210,7 +212,7 @@ __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2*
     return a;
 }
 
-// ---- runtime-radix fallback (any length whose prime factors are <= 31) -----------------------
+// ---- runtime-radix fallback (any length whose prime factors are <= PHD_MAX_PRIME) ------------
 template <int R>
 __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
                                         const float2* __restrict__ tw, int nbatch, int bstride) {
@@ -724,7 +726,7 @@ int phd_fft_plan_factors(int n, int* fac, int* nfac) {
     int odd[PHD_MAX_FACTORS], no = 0, tmp = n;
     for (int q = 3; tmp > 1 && q <= tmp; q += 2)
         while (tmp % q == 0) {
-            if (q > 31 || no >= PHD_MAX_FACTORS) return 1;  // large prime factor: not covered yet
+            if (q > PHD_MAX_PRIME || no >= PHD_MAX_FACTORS) return 1;  // huge prime factor: the O(p^2) butterfly is not meant for it
             odd[no++] = q;
             tmp /= q;
         }

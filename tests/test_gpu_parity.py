@@ -28,10 +28,10 @@ def test_group_id_of_all_2pow24_colours(ctx, oracle, kw):
     assert np.array_equal(got, want), f"FP64 path: {np.count_nonzero(got != want)} colours land in another group"
 
 
-@pytest.mark.parametrize("shape", [(1920, 1080), (3840, 2160), (6000, 4000), (405, 357), (1080, 1920), (350, 350)])
+@pytest.mark.parametrize("shape", [(1920, 1080), (3840, 2160), (6000, 4000), (405, 357), (1080, 1920), (350, 350), (752, 502)])
 def test_polar_bin_map_is_identical(ctx, oracle, shape):
     """bin ids (truncated PI, Newton sqrt, bottom-half row rule) and bin populations."""
-    assert all(_largest_prime(s) <= 31 for s in shape)  # lengths this build's radix set covers
+    assert all(_largest_prime(s) <= 1021 for s in shape)  # lengths this build's radix set covers
     m, c = ctx.debug_bin_map(*shape)
     mo, co = oracle.bin_map(*shape)
     assert np.array_equal(m, mo) and np.array_equal(c, co)
@@ -72,6 +72,7 @@ def test_report_matches_reference_golden(ctx, oracle, golden, name):
     (700, 525, 1, dict(h_partitions=9, s_partitions=3, v_partitions=4, coverage_thresh=0.9)),
     (1024, 768, 0, dict(downsample_rate=2, radius_partitions=16, angle_partitions=36)),
     (3840, 2160, 1, {}),   # BASELINE config 2: 4K with four salient boxes
+    (752, 502, 1, {}),     # 2^4*47 x 2*251: prime factors served by the O(p^2) butterfly of the generic FFT kernels
     # saliencies closer than 1 apart: the truncating comparator calls them equal (insertion-sort replay)
     (800, 600, 0, dict(quantity_weight=0.0, saturation_value_weight=1e-5)),
     (800, 600, 1, dict(quantity_weight=1e-6, saturation_value_weight=1e-6, coverage_thresh=0.5)),

@@ -215,7 +215,7 @@ __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2*
 // ---- runtime-radix fallback (any length whose prime factors are <= PHD_MAX_PRIME) ------------
 template <int R>
 __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
-                                        const float2* __restrict__ tw, int nbatch, int bstride) {
+                                        const float2* __restrict__ twp, int nbatch, int bstride) {
     const int m = n / R;
     const int total = nbatch * m;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -231,12 +231,13 @@ __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* _
         Radix<R>::run(x);
         y[R * pps + q] = x[0];
 #pragma unroll
-        for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf(x[j], __ldg(&tw[pps * j]));
+        for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf(x[j], __ldg(&twp[(j - 1) * m + b]));
     }
 }
 
+// other primes: O(r^2) butterfly straight from the definition
 __device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
-                              const float2* __restrict__ tw, int nbatch, int bstride) {
+                              const float2* __restrict__ tw, const float2* __restrict__ twp, int nbatch, int bstride) {
     const int m = n / r;
     const int total = nbatch * m;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
@@ -249,7 +250,7 @@ __device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __re
         for (int j = 0; j < r; j++) {
             float2 acc = a[b];
             for (int k = 1; k < r; k++) acc = caddf(acc, cmulf(a[b + k * m], __ldg(&tw[((j * k) % r) * m])));
-            y[r * pps + q + j * s] = j ? cmulf(acc, __ldg(&tw[pps * j])) : acc;
+            y[r * pps + q + j * s] = j ? cmulf(acc, __ldg(&twp[(j - 1) * m + b])) : acc;
         }
     }
 }
@@ -260,12 +261,21 @@ __device__ float2* fft_run_rt(const FftPlan& pl, float2* bufA, float2* bufB, int
     int s = 1;
     for (int f = 0; f < pl.nfac; f++) {
         const int r = pl.fac[f];
+        const float2* twp = pl.twp + pl.twp_off[f];
         switch (r) {
-            case 2: pass_rt<2>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            case 3: pass_rt<3>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            case 4: pass_rt<4>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            case 5: pass_rt<5>(a, b, pl.n, s, pl.tw, nbatch, bstride); break;
-            default: pass_rt_prime(r, a, b, pl.n, s, pl.tw, nbatch, bstride); break;
+            case 2: pass_rt<2>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 3: pass_rt<3>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 4: pass_rt<4>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 5: pass_rt<5>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 6: pass_rt<6>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 8: pass_rt<8>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 9: pass_rt<9>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 10: pass_rt<10>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 12: pass_rt<12>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 15: pass_rt<15>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 16: pass_rt<16>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 25: pass_rt<25>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            default: pass_rt_prime(r, a, b, pl.n, s, pl.tw, twp, nbatch, bstride); break;
         }
         __syncthreads();
         s *= r;
@@ -385,32 +395,66 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
     }
 }
 
-// Rows, generic: one CTA per row pair, runtime radix plan.
-__global__ void __launch_bounds__(kRowThreads) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
+// Rows, generic (any width, runtime radix plan): a CTA walks strided row quads.  The four rows' bytes are staged into
+// shared memory (16-byte vector loads when the rows are 16-byte aligned), each thread then converts "its" pixels of
+// both row pairs to gray numerators, two packed complex sequences are transformed, and every spectrum entry of the
+// quad leaves as one 32-byte sector.  Rows past the image bottom count as gray 0.5 (a zero sequence after the bias)
+// and land in the Hp padding of the transposed spectrum.
+__global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
                                                               float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);
-    float2* bufB = bufA + P.W;
-    const int img = blockIdx.y, pr = blockIdx.x;
-    const int ra = 2 * pr, rb = 2 * pr + 1;
-    const bool has_b = rb < P.H;
+    const int W = P.W;
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [2][W]
+    float2* bufB = bufA + 2 * W;                         // [2][W]; first holds the raw bytes of the quad (12 W <= 16 W)
+    unsigned char* raw = reinterpret_cast<unsigned char*>(bufB);
+    const int img = blockIdx.y;
+    const int nquads = P.Hp / 4;
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
-    const uint8_t* pa = base + (size_t)ra * P.W * 3;
-    const uint8_t* pb = base + (size_t)rb * P.W * 3;
-    for (int x = threadIdx.x; x < P.W; x += blockDim.x) {
-        const int ga = gray_num(pa + 3 * x);
-        const int gb = has_b ? gray_num(pb + 3 * x) : PHD_GRAY_BIAS;
-        bufA[x] = make_float2((float)(ga - PHD_GRAY_BIAS), (float)(gb - PHD_GRAY_BIAS));
-    }
-    __syncthreads();
-    const float2* z = fft_run_rt(pl, bufA, bufB, 1, 0);
-    float2* out = specT + (size_t)img * P.fw * P.Hp;
-    for (int k = threadIdx.x; k < P.fw; k += blockDim.x) {
-        const int kc = k == 0 ? 0 : P.W - k;
-        const float2 zk = z[k], zc = z[kc];
-        float2* o = out + (size_t)k * P.Hp + ra;
-        o[0] = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-        if (has_b) o[1] = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+    const int row_bytes = 3 * W;
+    const bool vec = P.aligned16 != 0 && (row_bytes % 16) == 0;
+    for (int q = blockIdx.x; q < nquads; q += gridDim.x) {
+        __syncthreads();  // the previous quad's output loop has finished reading bufB
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * q + r;
+            unsigned char* dst = raw + (size_t)r * row_bytes;
+            if (row >= P.H) continue;
+            const uint8_t* src = base + (size_t)row * row_bytes;
+            if (vec) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src);
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+            } else {
+                for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) dst[i] = __ldg(src + i);
+            }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 2 * W; idx += blockDim.x) {
+            const int pair = idx / W, x = idx - pair * W;
+            int g[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = 4 * q + 2 * pair + h;
+                const unsigned char* px = raw + (size_t)(2 * pair + h) * row_bytes + 3 * x;
+                g[h] = row < P.H ? 299 * (int)px[0] + 587 * (int)px[1] + 114 * (int)px[2] - PHD_GRAY_BIAS : 0;
+            }
+            bufA[idx] = make_float2((float)g[0], (float)g[1]);
+        }
+        __syncthreads();
+        const float2* z = fft_run_rt(pl, bufA, bufB, 2, W);
+        float2* out = specT + (size_t)img * P.fw * P.Hp + 4 * q;
+        for (int k = threadIdx.x; k < P.fw; k += blockDim.x) {
+            const int kc = k == 0 ? 0 : W - k;
+            float4 v[2];
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                const float2 zk = z[pr * W + k], zc = z[pr * W + kc];
+                v[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+            }
+            float* o = reinterpret_cast<float*>(out + (size_t)k * P.Hp);
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(v[0].x), "f"(v[0].y),
+                         "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z), "f"(v[1].w)
+                         : "memory");
+        }
     }
 }
 
@@ -598,7 +642,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
 
 // Columns, generic: runtime radix plan, plain loads, bin ids read from global memory.
 template <bool WRITE_POWER>
-__global__ void __launch_bounds__(kColThreads) k_cols_generic(DevParams P, FftPlan pl, int TC,
+__global__ void __launch_bounds__(kColThreads, 2) k_cols_generic(DevParams P, FftPlan pl, int TC,
                                                               const float2* __restrict__ specT,
                                                               const u16* __restrict__ binmapT,
                                                               const ImageAcc* __restrict__ iacc,
@@ -720,51 +764,87 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
 
 }  // namespace
 
-int phd_fft_plan_factors(int n, int* fac, int* nfac) {
-    int rem = n, k = 0;
-    // an odd radix first keeps the stride-R stores of the first pass conflict free
-    int odd[PHD_MAX_FACTORS], no = 0, tmp = n;
-    for (int q = 3; tmp > 1 && q <= tmp; q += 2)
-        while (tmp % q == 0) {
-            if (q > PHD_MAX_PRIME || no >= PHD_MAX_FACTORS) return 1;  // huge prime factor: the O(p^2) butterfly is not meant for it
-            odd[no++] = q;
-            tmp /= q;
-        }
-    for (int i = 0; i < no; i++) { fac[k++] = odd[i]; rem /= odd[i]; }
-    while (rem % 4 == 0) { if (k >= PHD_MAX_FACTORS) return 1; fac[k++] = 4; rem /= 4; }
-    while (rem % 2 == 0) { if (k >= PHD_MAX_FACTORS) return 1; fac[k++] = 2; rem /= 2; }
-    if (rem != 1) return 1;
-    *nfac = k;
-    return 0;
-}
-
 // Radix plans of the compile-time specialised lengths (must match the launch_*_t dispatch below).
 static bool special_radices(int n, int r[4]) {
     static const int tab[][5] = {{1920, 15, 8, 16, 1}, {3840, 15, 16, 16, 1}, {6000, 15, 25, 16, 1},
-                                 {1080, 9, 10, 12, 1},  {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1}};
+                                 {1080, 9, 10, 12, 1}, {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1}};
     for (const auto& t : tab)
         if (t[0] == n) { r[0] = t[1]; r[1] = t[2]; r[2] = t[3]; r[3] = t[4]; return true; }
     return false;
 }
 
-size_t phd_fft_pass_table_entries(int n) {
-    int r[4];
-    if (!special_radices(n, r)) return 0;
+// Radix plan of length n: the compile-time plan when n has one (the same pass tables then serve both kernel
+// families), otherwise few, large radices (16 15 12 10 9 8 6 5 4 3 2 have register butterflies; any other prime
+// up to PHD_MAX_PRIME gets the O(p^2) pass).  An odd radix goes first: its stride-R stores are conflict free.
+int phd_fft_plan_factors(int n, int* fac, int* nfac) {
+    int r4[4];
+    if (special_radices(n, r4)) {
+        int k = 0;
+        for (int i = 0; i < 4; i++) if (r4[i] > 1) fac[k++] = r4[i];
+        *nfac = k;
+        return 0;
+    }
+    int a2 = 0, a3 = 0, a5 = 0, k = 0, rem = n;
+    while (rem % 2 == 0) { a2++; rem /= 2; }
+    while (rem % 3 == 0) { a3++; rem /= 3; }
+    while (rem % 5 == 0) { a5++; rem /= 5; }
+    int odd[PHD_MAX_FACTORS], no = 0, even[PHD_MAX_FACTORS], ne = 0;
+    for (int q = 7; rem > 1 && q <= rem; q += 2)
+        while (rem % q == 0) {
+            if (q > PHD_MAX_PRIME || no >= PHD_MAX_FACTORS) return 1;  // the O(p^2) pass is not meant for huge primes
+            odd[no++] = q;
+            rem /= q;
+        }
+    if (rem != 1) return 1;
+    auto push = [&](int* arr, int& cnt, int v) { if (cnt < PHD_MAX_FACTORS) arr[cnt++] = v; };
+    while (a3 > 0 && a5 > 0) { push(odd, no, 15); a3--; a5--; }
+    while (a3 >= 2) { push(odd, no, 9); a3 -= 2; }
+    while (a5 >= 2) { push(odd, no, 25); a5 -= 2; }
+    if (a5 == 1) { if (a2 >= 1) { push(even, ne, 10); a2--; } else push(odd, no, 5); a5 = 0; }
+    if (a3 == 1) {
+        if (a2 >= 2) { push(even, ne, 12); a2 -= 2; }
+        else if (a2 == 1) { push(even, ne, 6); a2--; }
+        else push(odd, no, 3);
+        a3 = 0;
+    }
+    while (a2 >= 4) { push(even, ne, 16); a2 -= 4; }
+    if (a2 == 3) push(even, ne, 8);
+    else if (a2 == 2) push(even, ne, 4);
+    else if (a2 == 1) push(even, ne, 2);
+    if (no + ne > PHD_MAX_FACTORS) return 1;
+    // largest odd radix first, then everything else, big radices early
+    auto sort_desc = [](int* arr, int cnt) {
+        for (int i = 1; i < cnt; i++) for (int j = i; j > 0 && arr[j] > arr[j - 1]; j--) { int t = arr[j]; arr[j] = arr[j - 1]; arr[j - 1] = t; }
+    };
+    sort_desc(odd, no);
+    sort_desc(even, ne);
+    // a plain prime (O(p^2) pass) should not lead; prefer a register butterfly (15, 25, 9, 5, 3) in front
+    int lead = -1;
+    for (int i = 0; i < no; i++) if (odd[i] == 15 || odd[i] == 25 || odd[i] == 9 || odd[i] == 5 || odd[i] == 3) { lead = i; break; }
+    if (lead >= 0) fac[k++] = odd[lead];
+    for (int i = 0; i < ne; i++) fac[k++] = even[i];
+    for (int i = 0; i < no; i++) if (i != lead) fac[k++] = odd[i];
+    *nfac = k;
+    return 0;
+}
+
+size_t phd_fft_pass_table_entries(const FftPlan& pl) {
     size_t e = 0;
-    for (int i = 0; i < 4; i++) e += (size_t)(r[i] - 1) * (n / r[i]);
+    for (int f = 0; f < pl.nfac; f++) e += (size_t)(pl.fac[f] - 1) * (pl.n / pl.fac[f]);
     return e;
 }
 
-void phd_fft_fill_pass_tables(float2* dev, int n, cudaStream_t st) {
-    int r[4];
-    if (!special_radices(n, r)) return;
-    int s = 1;
-    for (int i = 0; i < 4; i++) {
-        const int cnt = (r[i] - 1) * (n / r[i]);
-        if (cnt > 0) k_pass_twiddles<<<(cnt + 255) / 256, 256, 0, st>>>(dev, n, r[i], s);
-        dev += cnt;
-        s *= r[i];
+void phd_fft_fill_pass_tables(float2* dev, FftPlan& pl, cudaStream_t st) {
+    int s = 1, off = 0;
+    for (int f = 0; f < pl.nfac; f++) {
+        const int r = pl.fac[f];
+        const int cnt = (r - 1) * (pl.n / r);
+        pl.twp_off[f] = off;
+        if (cnt > 0) k_pass_twiddles<<<(cnt + 255) / 256, 256, 0, st>>>(dev + off, pl.n, r, s);
+        off += cnt;
+        s *= r;
     }
+    pl.twp = dev;
 }
 
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st) {
@@ -785,20 +865,31 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
             case 6000: launch_rows_t<6000, 15, 25, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
         }
     }
-    const size_t smem = (size_t)P.W * 2 * sizeof(float2);
+    const size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
     if (smem > 200 * 1024) return 1;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_rows_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    k_rows_generic<<<dim3((P.H + 1) / 2, nimg), kRowThreads, smem, st>>>(rgb, P, row, specT);
+    {
+        const int nquads = P.Hp / 4;
+        int per_sm = (int)((220 * 1024) / smem);
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        long long want = (long long)per_sm * 148 * 4;
+        int gx = (int)((want + nimg - 1) / nimg);
+        if (gx > nquads) gx = nquads;
+        if (gx < 1) gx = 1;
+        // one CTA per SM when four rows need more than a third of the shared memory: give it 16 warps
+        k_rows_generic<<<dim3(gx, nimg), smem > 72 * 1024 ? 512 : kRowThreads, smem, st>>>(rgb, P, row, specT);
+    }
     return 0;
 }
 
 size_t phd_fft_cols_smem(const DevParams& P, int* tile_cols) {
     const size_t bins = (size_t)2 * P.nbins * sizeof(u32);
-    const size_t budget = 200 * 1024;
+    const size_t budget = 110 * 1024;  // two CTAs per SM
     int tc = 8;
     while (tc > 1 && (size_t)tc * P.Hp * 2 * sizeof(float2) + bins > budget) tc >>= 1;
     *tile_cols = tc;

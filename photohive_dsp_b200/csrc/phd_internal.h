@@ -77,8 +77,10 @@ struct FftPlan {
     int n;
     int nfac;
     int fac[PHD_MAX_FACTORS];
+    int twp_off[PHD_MAX_FACTORS];  // start of pass f's table inside twp
     const float2* tw;   // device, n entries exp(-2 pi i k / n)
-    const float2* twp;  // device, per-pass tables of the compile-time plan (fft.cu PlanT), or nullptr
+    const float2* twp;  // device, per-pass tables: pass f (radix r, m = n/r butterflies) reads
+                        // twp[twp_off[f] + (j-1)*m + b], j = 1..r-1 -- consecutive lanes, consecutive entries
 };
 
 // Device workspace for one sub-batch.
@@ -122,8 +124,8 @@ size_t phd_pixels_smem(const DevParams& P);
 
 int phd_fft_plan_factors(int n, int* fac, int* nfac);  // 0 ok, nonzero unsupported
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st);
-size_t phd_fft_pass_table_entries(int n);  // 0: n has no compile-time plan
-void phd_fft_fill_pass_tables(float2* dev, int n, cudaStream_t st);
+size_t phd_fft_pass_table_entries(const FftPlan& pl);
+void phd_fft_fill_pass_tables(float2* dev, FftPlan& pl, cudaStream_t st);  // also sets pl.twp_off / pl.twp
 int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* spec,
                         cudaStream_t st, int* launches);
 int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* spec, const u16* binmap,

@@ -241,22 +241,21 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
         return fail(ctx, PHD_E_UNSUPPORTED, "image side has a prime factor > 1021: FFT length not supported by this build");
     const int Hp = (H + 3) / 4 * 4;
     const size_t nspec = (size_t)(W / 2 + 1) * Hp;
-    const size_t pe_row = phd_fft_pass_table_entries(W), pe_col = phd_fft_pass_table_entries(H);
+    const size_t pe_row = phd_fft_pass_table_entries(s.row), pe_col = phd_fft_pass_table_entries(s.col);
     CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * (W + pe_row)));
     CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * (H + pe_col)));
     CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
     CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
     phd_fill_twiddles(s.tw_row, W, ctx->stream);
     phd_fill_twiddles(s.tw_col, H, ctx->stream);
-    phd_fft_fill_pass_tables(s.tw_row + W, W, ctx->stream);
-    phd_fft_fill_pass_tables(s.tw_col + H, H, ctx->stream);
+    phd_fft_fill_pass_tables(s.tw_row + W, s.row, ctx->stream);
+    phd_fft_fill_pass_tables(s.tw_col + H, s.col, ctx->stream);
     phd_launch_bin_map(W, H, Hp, nr, na, s.binmap, s.bincount, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     s.row.tw = s.tw_row;
     s.col.tw = s.tw_col;
-    s.row.twp = pe_row ? s.tw_row + W : nullptr;
-    s.col.twp = pe_col ? s.tw_col + H : nullptr;
+
     ctx->shapes.push_back(s);
     *out = &ctx->shapes.back();
     return PHD_OK;
@@ -389,7 +388,7 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         for (int b = 0; b < 2; b++)
             if ((rc = ensure_bytes(ctx, &ctx->d_stage[b], &ctx->d_stage_bytes[b], dev_stride * pb)) != PHD_OK) return rc;
     int tc;
-    if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
+    if ((size_t)P.W * 4 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
         return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
 
     cudaStream_t st = ctx->stream;

@@ -47,3 +47,7 @@ run("config2 4K + 4 boxes x128", W, H, 128, p, boxes)
 run("config4 24MP x64", 6000, 4000, 64, p)
 run("config5 fine palette 1080p x256", 1920, 1080, 256, make_params(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99))
 run("config3 1080p x512", 1920, 1080, 512, p)
+if "--generic" in sys.argv:
+    run("generic 4032x3024 x32 (runtime-radix FFT)", 4032, 3024, 32, p)
+    run("generic 5472x3648 x16", 5472, 3648, 16, p)
+    run("generic 1280x720 x256", 1280, 720, 256, p)

@@ -132,6 +132,42 @@ struct Composite {
         }
     }
 };
+// Odd prime P by the definition, folded on the conjugate symmetry W^(P-k) = conj(W^k): with s_k = x[k] + x[P-k],
+// d_k = x[k] - x[P-k],  X[j] = A_j + i B_j and X[P-j] = A_j - i B_j,  A_j = x0 + sum_k cos(jk) s_k,
+// B_j = sum_k TWS(jk) d_k  ((P-1)^2 FMAs in all, constants folded at compile time).
+template <int P>
+struct PrimeRadix {
+    static __device__ __forceinline__ void run(float2 (&x)[P]) {
+        constexpr int h = (P - 1) / 2;
+        float2 s[h], d[h];
+#pragma unroll
+        for (int k = 1; k <= h; k++) {
+            s[k - 1] = caddf(x[k], x[P - k]);
+            d[k - 1] = csubf(x[k], x[P - k]);
+        }
+        const float2 x0 = x[0];
+        float2 sum = x0;
+#pragma unroll
+        for (int k = 0; k < h; k++) sum = caddf(sum, s[k]);
+        x[0] = sum;
+#pragma unroll
+        for (int j = 1; j <= h; j++) {
+            float2 A = x0, B = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 1; k <= h; k++) {
+                const int e = (j * k) % P;
+                const float c = PhdTw<P>::c(e), t = PhdTw<P>::s(e);
+                A.x = fmaf(c, s[k - 1].x, A.x); A.y = fmaf(c, s[k - 1].y, A.y);
+                B.x = fmaf(t, d[k - 1].x, B.x); B.y = fmaf(t, d[k - 1].y, B.y);
+            }
+            x[j] = make_float2(A.x - B.y, A.y + B.x);
+            x[P - j] = make_float2(A.x + B.y, A.y - B.x);
+        }
+    }
+};
+template <> struct Radix<7> : PrimeRadix<7> {};
+template <> struct Radix<11> : PrimeRadix<11> {};
+template <> struct Radix<13> : PrimeRadix<13> {};
 template <> struct Radix<6> : Composite<2, 3> {};
 template <> struct Radix<8> : Composite<2, 4> {};
 template <> struct Radix<9> : Composite<3, 3> {};
@@ -249,7 +285,12 @@ __device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __re
         const int pps = b - q;
         for (int j = 0; j < r; j++) {
             float2 acc = a[b];
-            for (int k = 1; k < r; k++) acc = caddf(acc, cmulf(a[b + k * m], __ldg(&tw[((j * k) % r) * m])));
+            int e = 0;  // (j * k) % r, stepped
+            for (int k = 1; k < r; k++) {
+                e += j;
+                if (e >= r) e -= r;
+                acc = caddf(acc, cmulf(a[b + k * m], __ldg(&tw[e * m])));
+            }
             y[r * pps + q + j * s] = j ? cmulf(acc, __ldg(&twp[(j - 1) * m + b])) : acc;
         }
     }
@@ -268,10 +309,13 @@ __device__ float2* fft_run_rt(const FftPlan& pl, float2* bufA, float2* bufB, int
             case 4: pass_rt<4>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 5: pass_rt<5>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 6: pass_rt<6>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 7: pass_rt<7>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 8: pass_rt<8>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 9: pass_rt<9>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 10: pass_rt<10>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 11: pass_rt<11>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 12: pass_rt<12>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 13: pass_rt<13>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 15: pass_rt<15>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 16: pass_rt<16>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 25: pass_rt<25>(a, b, pl.n, s, twp, nbatch, bstride); break;

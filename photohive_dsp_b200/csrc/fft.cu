@@ -168,6 +168,8 @@ struct PrimeRadix {
 template <> struct Radix<7> : PrimeRadix<7> {};
 template <> struct Radix<11> : PrimeRadix<11> {};
 template <> struct Radix<13> : PrimeRadix<13> {};
+template <> struct Radix<17> : PrimeRadix<17> {};
+template <> struct Radix<19> : PrimeRadix<19> {};
 template <> struct Radix<6> : Composite<2, 3> {};
 template <> struct Radix<8> : Composite<2, 4> {};
 template <> struct Radix<9> : Composite<3, 3> {};
@@ -318,6 +320,8 @@ __device__ float2* fft_run_rt(const FftPlan& pl, float2* bufA, float2* bufB, int
             case 13: pass_rt<13>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 15: pass_rt<15>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 16: pass_rt<16>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 17: pass_rt<17>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 19: pass_rt<19>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 25: pass_rt<25>(a, b, pl.n, s, twp, nbatch, bstride); break;
             default: pass_rt_prime(r, a, b, pl.n, s, pl.tw, twp, nbatch, bstride); break;
         }

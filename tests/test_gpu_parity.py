@@ -74,6 +74,7 @@ def test_report_matches_reference_golden(ctx, oracle, golden, name):
     (3840, 2160, 1, {}),   # BASELINE config 2: 4K with four salient boxes
     (752, 502, 1, {}),     # 2^4*47 x 2*251: prime factors served by the O(p^2) butterfly of the generic FFT kernels
     (1008, 572, 0, {}),    # 2^4*3^2*7 x 2^2*11*13: register butterflies for the primes 7, 11 and 13
+    (646, 456, 1, {}),     # 2*17*19 x 2^3*3*19
     # saliencies closer than 1 apart: the truncating comparator calls them equal (insertion-sort replay)
     (800, 600, 0, dict(quantity_weight=0.0, saturation_value_weight=1e-5)),
     (800, 600, 1, dict(quantity_weight=1e-6, saturation_value_weight=1e-6, coverage_thresh=0.5)),

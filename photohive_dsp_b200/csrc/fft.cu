@@ -814,8 +814,13 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
 
 // Radix plans of the compile-time specialised lengths (must match the launch_*_t dispatch below).
 static bool special_radices(int n, int r[4]) {
-    static const int tab[][5] = {{1920, 15, 8, 16, 1}, {3840, 15, 16, 16, 1}, {6000, 15, 25, 16, 1},
-                                 {1080, 9, 10, 12, 1}, {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1}};
+    static const int tab[][5] = {{1920, 15, 8, 16, 1}, {3840, 15, 16, 16, 1}, {6000, 15, 25, 16, 1},   // BASELINE rows
+                                 {1080, 9, 10, 12, 1}, {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1},   // BASELINE columns
+                                 // common video / camera sizes (rows, then columns)
+                                 {1280, 5, 16, 16, 1}, {2560, 10, 16, 16, 1}, {1024, 4, 16, 16, 1}, {2048, 8, 16, 16, 1},
+                                 {800, 5, 10, 16, 1},  {640, 5, 8, 16, 1},
+                                 {720, 9, 10, 8, 1},   {1440, 9, 10, 16, 1},  {768, 3, 16, 16, 1},  {1536, 6, 16, 16, 1},
+                                 {600, 15, 8, 5, 1},   {480, 15, 8, 4, 1}};
     for (const auto& t : tab)
         if (t[0] == n) { r[0] = t[1]; r[1] = t[2]; r[2] = t[3]; r[3] = t[4]; return true; }
     return false;
@@ -900,7 +905,8 @@ void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st) {
 }
 
 static bool rows_fast_ok(const DevParams& P) {
-    return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && (P.W == 1920 || P.W == 3840 || P.W == 6000);
+    int r[4];
+    return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && special_radices(P.W, r);
 }
 
 int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* specT,
@@ -911,6 +917,12 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
             case 1920: launch_rows_t<1920, 15, 8, 16, 1, PHD_ROWS_PAIRS_1920>(rgb, P, nimg, row.twp, specT, st); return 0;
             case 3840: launch_rows_t<3840, 15, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
             case 6000: launch_rows_t<6000, 15, 25, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 1280: launch_rows_t<1280, 5, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 2560: launch_rows_t<2560, 10, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 1024: launch_rows_t<1024, 4, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 2048: launch_rows_t<2048, 8, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 800: launch_rows_t<800, 5, 10, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+            case 640: launch_rows_t<640, 5, 8, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
         }
     }
     const size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
@@ -952,6 +964,12 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
             case 1080: launch_cols_t<1080, 9, 10, 12, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 720: launch_cols_t<720, 9, 10, 8, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 1440: launch_cols_t<1440, 9, 10, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 768: launch_cols_t<768, 3, 16, 16, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 1536: launch_cols_t<1536, 6, 16, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 600: launch_cols_t<600, 15, 8, 5, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 480: launch_cols_t<480, 15, 8, 4, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
         }
     }
     int tc;

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
     unsigned char* tb_raw = smem_raw;
     u16* tie_cache = reinterpret_cast<u16*>(smem_raw + phd_cell_tables_bytes());  // [chunk] tie index of each pixel
     u16* tie_of_pair = tie_cache + P.chunk;                                       // [ncls*hp] (cls, hue bin) -> tie index
+    unsigned char* cls_has_tie = reinterpret_cast<unsigned char*>(tie_of_pair + P.ncls * P.hp);  // [ncls]
     constexpr u16 NONE = 0xffff;
     __shared__ GroupPlan tplan[MAXT];
     __shared__ int scan[256];
@@ -389,15 +390,21 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
             cur_img = img;
             nt = tie_n[img];
             for (int i = tid; i < npairs; i += 256) tie_of_pair[i] = NONE;
+            for (int i = tid; i < P.ncls; i += 256) cls_has_tie[i] = 0;
             for (int k = tid; k < min(nt, MAXT); k += 256) tplan[k] = plan_g[(size_t)img * T + tie_list[(size_t)img * T + k]];
             __syncthreads();
             for (int k = 0; k < nt; k++) {
                 const int g = tie_list[(size_t)img * T + k];
                 if (g < P.hp * spvp) {
-                    if (tid == 0) { const int j = g / spvp, cls = g - j * spvp; tie_of_pair[cls * P.hp + j] = (u16)k; }
+                    if (tid == 0) {
+                        const int j = g / spvp, cls = g - j * spvp;
+                        tie_of_pair[cls * P.hp + j] = (u16)k;
+                        cls_has_tie[cls] = 1;
+                    }
                 } else {
                     const int cls = (g == T - 1) ? spvp + 1 : spvp;
                     for (int j = tid; j < P.hp; j += 256) tie_of_pair[cls * P.hp + j] = (u16)k;
+                    if (tid == 0) cls_has_tie[cls] = 1;
                 }
             }
             __syncthreads();
@@ -422,9 +429,13 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
                         const uint8_t* q = base + phd_src_index(c0 + li, P) * 3;
                         R = __ldg(q); G = __ldg(q + 1); B = __ldg(q + 2);
                     }
-                    const PixOut o = phd_pixel(R, G, B, svtab, K, exc);
-                    t = tie_of_pair[o.cell >> 2];
-                    if (t != NONE && chunk < get_plan(t).cstar) accept(ct, o);  // whole chunk accepted
+                    // most pixels are ruled out by their saturation/value class alone: (max, min) -> class
+                    const int mx = max(R, max(G, B)), mn = min(R, min(G, B));
+                    if (cls_has_tie[svtab[((mx * mx + mx) >> 1) + mn]]) {
+                        const PixOut o = phd_pixel(R, G, B, svtab, K, exc);
+                        t = tie_of_pair[o.cell >> 2];
+                        if (t != NONE && chunk < get_plan(t).cstar) accept(ct, o);  // whole chunk accepted
+                    }
                 }
                 tie_cache[li] = t;
             }
@@ -610,7 +621,7 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
 
 void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                              const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
-    const size_t smem = phd_cell_tables_bytes() + ((size_t)P.chunk + (size_t)P.ncls * P.hp) * sizeof(u16);
+    const size_t smem = phd_cell_tables_bytes() + ((size_t)P.chunk + (size_t)P.ncls * P.hp) * sizeof(u16) + (size_t)P.ncls + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_palette_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -11,7 +11,7 @@ from .structures import (Blur_Profile, Crop_Boundaries, Full_Report_Data, Image_
                          phd_params)
 
 directory = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(directory, "PhotoHive_DSP_lib", "libreport_data.so")
+lib_path = os.environ.get("PHD_LIB_PATH") or os.path.join(directory, "PhotoHive_DSP_lib", "libreport_data.so")  # override: A/B runs
 
 if not os.path.exists(lib_path):
     raise ImportError(

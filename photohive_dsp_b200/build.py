@@ -43,6 +43,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
               "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         common += ["-Xptxas", "-v"]
+    common += os.environ.get("PHD_NVCC_EXTRA", "").split()  # experiments: extra -D... / -Xptxas flags
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))

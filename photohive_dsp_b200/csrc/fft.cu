@@ -37,7 +37,10 @@ constexpr int kRowThreads = 256;
 #ifndef PHD_ROWS_PAIRS_1920
 #define PHD_ROWS_PAIRS_1920 2
 #endif
-constexpr int kColThreads = 512;
+#ifndef PHD_EXP_COLTHREADS
+#define PHD_EXP_COLTHREADS 512
+#endif
+constexpr int kColThreads = PHD_EXP_COLTHREADS;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -774,7 +777,10 @@ void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float
     if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
     if (per_sm < 1) per_sm = 1;
     const int nsteps = P.H / (2 * PAIRS);
-    long long want = (long long)per_sm * 148 * 4;
+#ifndef PHD_EXP_ROWWAVES
+#define PHD_EXP_ROWWAVES 4
+#endif
+    long long want = (long long)per_sm * 148 * PHD_EXP_ROWWAVES;
     int gx = (int)((want + nimg - 1) / nimg);
     if (gx > nsteps) gx = nsteps;
     if (gx < 1) gx = 1;

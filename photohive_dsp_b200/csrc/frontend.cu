@@ -19,6 +19,11 @@
 
 namespace {
 
+#ifndef PHD_EXP_UNROLL
+#define PHD_EXP_UNROLL 15  // the 15 pixels after the first: fully unrolled
+#endif
+constexpr int kPixUnroll = PHD_EXP_UNROLL;
+
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
                 const PixOut o = phd_pixel(packed_byte(w, 0), packed_byte(w, 1), packed_byte(w, 2), svtab, K, exc);
                 run.addr = cw_base + 4u * (u32)o.cell; run.w0 = o.w0; run.mx = o.mx; run.s = o.sbits; run.h = o.hbits;
             }
-#pragma unroll
+#pragma unroll kPixUnroll
             for (int i = 1; i < 16; i++)
                 run_step<4 * NCS>(run, cw_base, scratch, stride_b,
                                   phd_pixel(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1), packed_byte(w, 3 * i + 2),
@@ -600,7 +605,10 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
     // chunks per CTA: long walks amortise the table load and the final flush; enough CTAs to fill 148 SMs
     long long total = (long long)P.nchunks * nimg;
     int cpp = (int)(total / (148 * 12));
-    cpp = cpp < 1 ? 1 : (cpp > 32 ? 32 : cpp);
+#ifndef PHD_EXP_CPPCAP
+#define PHD_EXP_CPPCAP 32
+#endif
+    cpp = cpp < 1 ? 1 : (cpp > PHD_EXP_CPPCAP ? PHD_EXP_CPPCAP : cpp);
     dim3 grid((P.nchunks + cpp - 1) / cpp, nimg);
     const bool ds = P.ds > 1;
     if (P.fe_threads == 256) {

@@ -184,6 +184,14 @@ def main():
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: run on (and first-touch the pinned staging buffers from) the CPUs next to this GPU
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = "gpu-local cpus"
+    except Exception as e:  # affinity is a host-side nicety, never a reason to fail the measurement
+        numa = f"not set ({type(e).__name__})"
     if world > 1:
         # keep stdout to the one JSON line: NCCL's version banner goes there at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -290,7 +298,7 @@ def main():
                        "wall_ms_per_step": 1000.0 * wall_s / args.steps, "sub_batch": os.environ.get("PHD_SUB_BATCH", "auto")},
             "e2e": {"value": eb * world * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": eb * stride,
                     "d2h_bytes_per_step": eb * lay.record_bytes, "batch": eb, "records_identical_to_device_run": same,
-                    "path": "phd_get_reports_u8 (C ABI) with pinned host buffers"},
+                    "path": "phd_get_reports_u8 (C ABI) with pinned host buffers", "cpu_affinity": numa},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -654,10 +654,11 @@ void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const
     else k_group_sweep<false><<<(1 << 24) / 256, 256, 256 * sizeof(double), st>>>(P, tabs, exc, out_dev);
 }
 
+// exc_dev == nullptr: the exceptional-colour codes of this h_partitions already exist (they depend on nothing else)
 void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev, unsigned char* exc_dev, int* ok_dev,
                                   cudaStream_t st) {
     k_build_cell_tables<<<1, 256, 0, st>>>(P, tables_dev, ok_dev);
-    k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
+    if (exc_dev) k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
 }
 
 size_t phd_cell_tables_size() { return phd_cell_tables_bytes(); }

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "phd_internal.h"
@@ -29,7 +30,8 @@ struct ParamTables {
     double* centres = nullptr;  // device [3*T]: group centre h, s, v
     float* sv_f = nullptr;      // device [T]: (float)(s*v) of the centre
     unsigned char* tabs = nullptr;  // device: class / reciprocal tables of pixel_cells.cuh
-    unsigned char* exc = nullptr;   // device: 2^24 exceptional-colour codes (pixel_cells.cuh)
+    unsigned char* exc = nullptr;   // device: 2^24 exceptional-colour codes (pixel_cells.cuh); shared by every
+                                    // parameter set with the same h_partitions, owned by phd_context::exc_tables
 };
 
 }  // namespace
@@ -40,6 +42,7 @@ struct phd_context {
     std::mutex mu;
     std::vector<ShapePlan> shapes;
     std::vector<ParamTables> tables;
+    std::vector<std::pair<int, unsigned char*>> exc_tables;  // (h_partitions, 16 MB code table)
     Workspace ws{};
     unsigned char* ws_zero = nullptr;  // one allocation holding every accumulator that must start at zero
     size_t ws_zero_bytes = 0;
@@ -215,17 +218,24 @@ int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
     int* ok_dev = nullptr;
     int ok = 1;
     CUDA_TRY(ctx, cudaMalloc(&t.tabs, phd_cell_tables_size()));
-    CUDA_TRY(ctx, cudaMalloc(&t.exc, (size_t)1 << 24));
+    unsigned char* new_exc = nullptr;
+    for (auto& e : ctx->exc_tables)
+        if (e.first == hp) t.exc = e.second;
+    if (!t.exc) {
+        CUDA_TRY(ctx, cudaMalloc(&new_exc, (size_t)1 << 24));
+        t.exc = new_exc;
+    }
     CUDA_TRY(ctx, cudaMalloc(&ok_dev, sizeof(int)));
     CUDA_TRY(ctx, cudaMemcpyAsync(ok_dev, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    phd_launch_build_cell_tables(P, t.tabs, t.exc, ok_dev, ctx->stream);
+    phd_launch_build_cell_tables(P, t.tabs, new_exc, ok_dev, ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(&ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(ok_dev);
     if (!ok) {
-        cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); cudaFree(t.exc);
+        cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); cudaFree(new_exc);
         return fail(ctx, PHD_E_UNSUPPORTED, "thresholds put a colour outside the palette grid (the reference would index past it)");
     }
+    if (new_exc) ctx->exc_tables.push_back({hp, new_exc});
     ctx->tables.push_back(t);
     *out = &ctx->tables.back();
     return PHD_OK;
@@ -581,7 +591,8 @@ void phd_context_destroy(phd_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->shapes) { cudaFree(s.tw_row); cudaFree(s.tw_col); cudaFree(s.binmap); cudaFree(s.bincount); }
-    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); cudaFree(t.exc); }
+    for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); }
+    for (auto& e : ctx->exc_tables) cudaFree(e.second);
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);

@@ -767,11 +767,7 @@ template <int N, int R0, int R1, int R2, int R3, int PAIRS>
 void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
     constexpr int THREADS = ((PAIRS * (N / 16) + 127) / 128) * 128;  // one 16-pixel staging task per thread
     const size_t smem = (size_t)PAIRS * (2 * N + N / 16) * sizeof(float2);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    PHD_ALLOW_SMEM((k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS>), (int)smem);
     // CTAs walk strided steps; about four resident waves keep the tail short
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
@@ -791,12 +787,8 @@ template <int N, int R0, int R1, int R2, int R3, int NB>
 void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
                    Workspace& ws, float* power_out, cudaStream_t st) {
     const size_t smem = (size_t)2 * NB * N * sizeof(float2) + (size_t)2 * NB * N * sizeof(u16) + (size_t)2 * P.nbins * sizeof(u32);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_cols_t<N, R0, R1, R2, R3, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_cols_t<N, R0, R1, R2, R3, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
-    }
+    PHD_ALLOW_SMEM((k_cols_t<N, R0, R1, R2, R3, NB, false>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_cols_t<N, R0, R1, R2, R3, NB, true>), 200 * 1024);
     // groups per CTA: long walks amortise the bin zero/flush; pick the walk length whose CTA count fills whole
     // waves of the machine (2 CTAs of this size per SM, 148 SMs)
     const int ngroups = (P.fw + NB - 1) / NB;
@@ -933,11 +925,7 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
     }
     const size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
     if (smem > 200 * 1024) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_rows_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_rows_generic), 200 * 1024);
     {
         const int nquads = P.Hp / 4;
         int per_sm = (int)((220 * 1024) / smem);
@@ -981,12 +969,8 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
     int tc;
     const size_t smem = phd_fft_cols_smem(P, &tc);
     if (smem > 200 * 1024) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_cols_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_cols_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_cols_generic<false>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_cols_generic<true>), 200 * 1024);
     dim3 grid((P.fw + tc - 1) / tc, nimg);
     if (power_out)
         k_cols_generic<true><<<grid, kColThreads, smem, st>>>(P, col, tc, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out);

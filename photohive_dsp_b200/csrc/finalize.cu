@@ -191,11 +191,7 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
 void phd_launch_finalize(const DevParams& P, int nimg, const double* centres, const int* bincount, Workspace& ws,
                          const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches) {
     const size_t smem = ((size_t)P.nbins + 2 * (size_t)P.na) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_finalize), 200 * 1024);
     k_finalize<<<nimg, 256, smem, st>>>(P, centres, bincount, ws.iacc, ws.pal_n, ws.parent_ids, ws.sacc, ws.plan,
                                         ws.tie_list, ws.tie_n, ws.cells_tie, ws.binsum,
                                         ws.maxpow, ws.sharp, ws.boxes, ws.tie_groups, ws.dropped, lay, records_dev);

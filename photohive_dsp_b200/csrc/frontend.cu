@@ -594,14 +594,10 @@ size_t phd_pixels_smem(const DevParams& P) {
 void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                        const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
     const size_t smem = phd_pixels_smem(P);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_pixels<256, false, PHD_NCS_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_pixels<256, true, PHD_NCS_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_pixels<512, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_pixels<512, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_pixels<256, false, PHD_NCS_SMALL, true>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_pixels<256, true, PHD_NCS_SMALL, true>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_pixels<512, false, 0, false>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_pixels<512, true, 0, false>), 200 * 1024);
     // chunks per CTA: long walks amortise the table load and the final flush; enough CTAs to fill 148 SMs
     long long total = (long long)P.nchunks * nimg;
     int cpp = (int)(total / (148 * 12));
@@ -630,11 +626,7 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
 void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                              const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
     const size_t smem = phd_cell_tables_bytes() + ((size_t)P.chunk + (size_t)P.ncls * P.hp) * sizeof(u16) + (size_t)P.ncls + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_palette_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_palette_ties), 200 * 1024);
     int grid = nimg * 4;
     if (grid > 148 * 4) grid = 148 * 4;
     k_palette_ties<<<grid, 256, smem, st>>>(rgb, P, tabs, exc, ws.plan, ws.tie_list, ws.tie_n, ws.work, ws.work_n,
@@ -645,11 +637,7 @@ void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, c
 void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const unsigned char* exc, bool fast,
                             u16* out_dev, cudaStream_t st) {
     const size_t smem = 256 * sizeof(double) + phd_cell_tables_bytes();
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_group_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_group_sweep<true>), 100 * 1024);
     if (fast) k_group_sweep<true><<<(1 << 24) / 256, 256, smem, st>>>(P, tabs, exc, out_dev);
     else k_group_sweep<false><<<(1 << 24) / 256, 256, 256 * sizeof(double), st>>>(P, tabs, exc, out_dev);
 }

@@ -346,11 +346,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
                                cudaStream_t st, int* launches) {
     const size_t smem = (size_t)P.T * 11 * sizeof(int) + (size_t)((P.nchunks + 31) / 32) * sizeof(u32);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_palette_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    PHD_ALLOW_SMEM((k_palette_select), 200 * 1024);
     k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.cells, ws.counts_chunk, ws.plan, ws.pal_n,
                                               ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped, ws.sacc,
                                               ws.hist, ws.iacc, ws.cells_tie, ws.work, ws.work_n);

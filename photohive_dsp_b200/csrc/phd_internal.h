@@ -18,6 +18,19 @@
 #define PHD_T_SHIFT 22        // wrapped hue sums per parent: degrees * 2^22
 #define PHD_LN_SHIFT 20       // ln(power): value * 2^20 (value < 2^6)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the function IN THE CURRENT
+// DEVICE'S context, so it is set once per device (a process may hold contexts on several GPUs).
+#define PHD_ALLOW_SMEM(func, bytes)                                                                           \
+    do {                                                                                                      \
+        static bool done_[64];                                                                                \
+        int d_ = 0;                                                                                           \
+        cudaGetDevice(&d_);                                                                                   \
+        if ((unsigned)d_ < 64u && !done_[d_]) {                                                               \
+            cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
+            done_[d_] = true;                                                                                 \
+        }                                                                                                     \
+    } while (0)
+
 typedef unsigned long long u64;
 typedef unsigned int u32;
 typedef unsigned short u16;

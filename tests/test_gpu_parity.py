@@ -148,6 +148,23 @@ def test_device_resident_input_equals_host_input(ctx, oracle):
     assert np.array_equal(host.raw, dev.raw)
 
 
+def test_two_devices_in_one_process(ctx, oracle):
+    """One context per GPU inside ONE process (the library allows it): same records from both devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from photohive_dsp_b200.batch import Context
+    imgs = np.stack([oracle.generate(k % 3, 500 + k, 1920, 1080) for k in range(2)] )
+    a = ctx.get_reports(imgs)
+    other = Context(1)
+    try:
+        b = other.get_reports(imgs)
+        c = other.get_reports(torch.from_numpy(imgs).to("cuda:1"))
+    finally:
+        other.close()
+    assert np.array_equal(a.raw, b.raw) and np.array_equal(a.raw, c.raw)
+
+
 def test_edge_images(ctx, oracle):
     """Flat, black, white and two-colour images: empty spectrum, single group, max==1 clamps."""
     H, W = 400, 560

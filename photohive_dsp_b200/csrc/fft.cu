@@ -41,6 +41,9 @@ constexpr int kRowThreads = 256;
 #define PHD_EXP_COLTHREADS 512
 #endif
 constexpr int kColThreads = PHD_EXP_COLTHREADS;
+#ifndef PHD_COLS_GT
+#define PHD_COLS_GT 0
+#endif
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -200,15 +203,28 @@ __device__ __forceinline__ int pad16(int e) { return e + (e >> 4); }
 // One Stockham pass, compile-time length N, radix R, stride S (product of the radices already applied), over
 // nfft sequences laid out fstride apart in shared memory.  Reads are unit stride across lanes; the first pass
 // (S == 1) writes with stride R, which is why the plans start with an odd radix (conflict-free 8-byte stores).
-template <int N, int R, int S, bool PADIN>
+// GT > 0: the CTA is split into groups of GT threads and group f owns sequence f for the whole transform, so the
+// passes of one sequence synchronise on a NAMED barrier of GT threads (bar.sync 1+f) instead of the whole CTA:
+// warps only ever wait for the siblings that work on the same sequence.  GT == 0: all threads share all sequences.
+template <int GT>
+__device__ __forceinline__ void seq_sync() {
+    if (GT == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / GT), "n"(GT) : "memory");
+}
+
+template <int N, int R, int S, bool PADIN, int GT>
 __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
                                        const float2* __restrict__ twp, int nfft, int fstride_in, int fstride_out) {
     constexpr int M = N / R;
     static_assert(!PADIN || M % 16 == 0, "padded input needs M % 16 == 0");
-    const int total = nfft * M;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int f = idx / M;
-        const int b = idx - f * M;
+    const int total = GT > 0 ? M : nfft * M;
+    const int first = GT > 0 ? (int)threadIdx.x % GT : (int)threadIdx.x;
+    const int step = GT > 0 ? GT : (int)blockDim.x;
+    const int f_fixed = GT > 0 ? (int)threadIdx.x / GT : 0;
+    if (GT > 0 && f_fixed >= nfft) return;
+    for (int idx = first; idx < total; idx += step) {
+        const int f = GT > 0 ? f_fixed : idx / M;
+        const int b = idx - (GT > 0 ? 0 : f * M);
         const int q = b % S;
         const int pps = b - q;
         const float2* a = in + f * fstride_in;
@@ -235,21 +251,21 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
 }
 
 // Up to four passes; R3 == 1 means a three-pass plan.  a: input (padded layout when PADIN), b: scratch.
-// Returns the buffer holding the result (unpadded, sequences fstride apart).
-template <int N, int R0, int R1, int R2, int R3, bool PADIN>
+// Returns the buffer holding the result (unpadded, sequences fstride apart).  The barrier after the LAST pass is
+// left to the caller (it usually needs a CTA-wide one there anyway).
+template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT>
 __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ twp, int nfft,
                                              int fstride_a, int fstride) {
     static_assert(R0 * R1 * R2 * R3 == N, "radix plan does not multiply to N");
     using PL = PlanT<N, R0, R1, R2, R3>;
-    pass_t<N, R0, 1, PADIN>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
-    __syncthreads();
-    pass_t<N, R1, R0, false>(b, a, twp + PL::off1, nfft, fstride, fstride);
-    __syncthreads();
-    pass_t<N, R2, R0 * R1, false>(a, b, twp + PL::off2, nfft, fstride, fstride);
-    __syncthreads();
+    pass_t<N, R0, 1, PADIN, GT>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
+    seq_sync<GT>();
+    pass_t<N, R1, R0, false, GT>(b, a, twp + PL::off1, nfft, fstride, fstride);
+    seq_sync<GT>();
+    pass_t<N, R2, R0 * R1, false, GT>(a, b, twp + PL::off2, nfft, fstride, fstride);
     if (R3 == 1) return b;
-    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false>(b, a, twp + PL::off3, nfft, fstride, fstride);
-    __syncthreads();
+    seq_sync<GT>();
+    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false, GT>(b, a, twp + PL::off3, nfft, fstride, fstride);
     return a;
 }
 
@@ -395,10 +411,10 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
     // its pair (2 x three 16-byte loads).  The loads of the next step are issued before the passes of this one and
     // stay in registers meanwhile.
     constexpr int SEGS = N / 16;
-    static_assert(PAIRS * SEGS <= THREADS, "one staging task per thread");
-    const int task = threadIdx.x;
-    const bool has_task = task < PAIRS * SEGS;
-    const int pair = task / SEGS, seg = task - pair * SEGS;
+    constexpr int GT = THREADS / PAIRS;  // threads of one pair: they stage, transform and synchronise among themselves
+    static_assert(SEGS <= GT && GT % 32 == 0, "one staging task per thread of the pair's group");
+    const int pair = threadIdx.x / GT, seg = threadIdx.x % GT;
+    const bool has_task = seg < SEGS;
     uint4 a0, b0, c0, a1, b1, c1;
     auto load_step = [&](int q) {
         const uint8_t* base = img_base + (size_t)(2 * PAIRS * q) * N * 3;
@@ -418,8 +434,9 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
             for (int i = 0; i < 16; i++) dst[i] = make_float2((float)gray16(w0, i), (float)gray16(w1, i));
             if (q + q_step < q_end) load_step(q + q_step);
         }
-        __syncthreads();
-        const float2* z = fft_run_t<N, R0, R1, R2, R3, true>(bufA, bufB, twp, PAIRS, NP, N);
+        __syncthreads();  // CTA wide: the previous step's output loop (all threads read every pair's result) is over
+        const float2* z = fft_run_t<N, R0, R1, R2, R3, true, GT>(bufA, bufB, twp, PAIRS, NP, N);
+        __syncthreads();  // every pair's spectrum is complete
         float2* out = specT + (size_t)img * fw * P.Hp + 2 * PAIRS * q;
         for (int k = threadIdx.x; k < fw; k += blockDim.x) {
             const int kc = k == 0 ? 0 : N - k;
@@ -673,7 +690,8 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
         const int it = g - g_begin;
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         mbar_wait(&bar, it & 1);
-        float2* res = fft_run_t<N, R0, R1, R2, R3, false>(bufA, bufB, tw, ncol, N, N);  // ends with a CTA barrier
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false, PHD_COLS_GT>(bufA, bufB, tw, ncol, N, N);
+        __syncthreads();
         if (threadIdx.x == 0) {
             if (g + 1 < g_end) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // bufA was written by pass 2

@@ -41,8 +41,8 @@ constexpr int kRowThreads = 256;
 #define PHD_EXP_COLTHREADS 512
 #endif
 constexpr int kColThreads = PHD_EXP_COLTHREADS;
-#ifndef PHD_COLS_GT
-#define PHD_COLS_GT 0
+#ifndef PHD_COLS_GROUPS
+#define PHD_COLS_GROUPS 1  // one named-barrier thread group per column (see seq_sync)
 #endif
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
         const int it = g - g_begin;
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         mbar_wait(&bar, it & 1);
-        float2* res = fft_run_t<N, R0, R1, R2, R3, false, PHD_COLS_GT>(bufA, bufB, tw, ncol, N, N);
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false, PHD_COLS_GROUPS ? kColThreads / NB : 0>(bufA, bufB, tw, ncol, N, N);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (g + 1 < g_end) {

@@ -575,15 +575,18 @@ __device__ __forceinline__ void cols_fix_dc(const DevParams& P, const ImageAcc* 
 
 // power -> (p < 1 ? 0 : ln p) as fixed point 2^-20 -> polar bin, run-length merged per thread (bins change slowly
 // along a column) into the shared integer bins.  Returns the running max of the RAW power (re^2 + im^2).
-template <int SEG>
+// GT > 0: column c belongs to the thread group c (threads c*GT .. c*GT+GT-1, the group that transformed it).
+template <int SEG, int GT>
 __device__ __forceinline__ float cols_accumulate(int H, int ncol, const float2* res, int cs, const u16* map, int ms,
                                                  u32* bin_lo, u32* bin_hi, float mymax) {
     const float thr = (float)PHD_POWER_SCALE;                            // p >= 1  <=>  raw >= 255000^2
     const float lg2c = (float)(-2.0 * 17.960137721520944);               // log2(1 / 255000^2)
     const float kq = (float)(0.69314718055994530942 * (1 << PHD_LN_SHIFT));  // ln 2 * 2^20
     const int segs = (H + SEG - 1) / SEG;
-    for (int task = threadIdx.x; task < ncol * segs; task += blockDim.x) {
-        const int c = task / segs, k0 = (task - c * segs) * SEG;
+    const int first = GT > 0 ? (int)threadIdx.x % GT : (int)threadIdx.x;
+    const int total = GT > 0 ? ((int)threadIdx.x / GT < ncol ? segs : 0) : ncol * segs;
+    for (int task = first; task < total; task += (GT > 0 ? GT : (int)blockDim.x)) {
+        const int c = GT > 0 ? (int)threadIdx.x / GT : task / segs, k0 = (task - (GT > 0 ? 0 : c * segs)) * SEG;
         const float2* rp = res + c * cs + k0;
         const u16* mp = map + c * ms + k0;
         int run_bin = -1;
@@ -659,6 +662,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
                                                         const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
                                                         u32* __restrict__ maxpow, float* __restrict__ power_out, int gpc) {
     static_assert(R3 == 1, "the prefetch below assumes the result lands in bufB");
+    constexpr int GT = PHD_COLS_GROUPS ? kColThreads / NB : 0;  // thread group of one column (see seq_sync)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + NB * N;
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
         const int it = g - g_begin;
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         mbar_wait(&bar, it & 1);
-        float2* res = fft_run_t<N, R0, R1, R2, R3, false, PHD_COLS_GROUPS ? kColThreads / NB : 0>(bufA, bufB, tw, ncol, N, N);
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT>(bufA, bufB, tw, ncol, N, N);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (g + 1 < g_end) {
@@ -702,9 +706,14 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
         if (WRITE_POWER) cols_write_power(P, img, x0, ncol, res, N, power_out);
         else {
             constexpr int SEG = (NB * N + kColThreads - 1) / kColThreads;
-            mymax = cols_accumulate<SEG>(P.H, ncol, res, N, smap + (it & 1) * NB * N, N, bin_lo, bin_hi, mymax);
+            mymax = cols_accumulate<SEG, GT>(P.H, ncol, res, N, smap + (it & 1) * NB * N, N, bin_lo, bin_hi, mymax);
         }
-        __syncthreads();  // bufB is rewritten by the next group's first pass
+        // bufB is rewritten by the next group's first pass: a column is binned and rewritten by the thread group
+        // that transformed it, so the hand-over is that group's barrier (the test hook spreads its writes over
+        // all threads).  The only CTA-wide barrier of the loop is the one above that frees bufA for the prefetch;
+        // giving each group its own mbarrier and prefetch removes that one too but measured 0.5% slower.
+        if (WRITE_POWER) __syncthreads();
+        else seq_sync<GT>();
     }
     if (!WRITE_POWER) cols_flush(P, img, mymax, bin_lo, bin_hi, sh_max, binsum, maxpow);
 }
@@ -739,7 +748,7 @@ __global__ void __launch_bounds__(kColThreads, 2) k_cols_generic(DevParams P, Ff
         return;
     }
     if (x0 == 0 && threadIdx.x == 0) cols_fix_dc(P, iacc, img, res);  // thread 0 also owns point (0,0) below
-    const float mymax = cols_accumulate<8>(P.H, ncol, res, Hp, binmapT + (size_t)x0 * Hp, Hp, bin_lo, bin_hi, 0.f);
+    const float mymax = cols_accumulate<8, 0>(P.H, ncol, res, Hp, binmapT + (size_t)x0 * Hp, Hp, bin_lo, bin_hi, 0.f);
     __syncthreads();
     cols_flush(P, img, mymax, bin_lo, bin_hi, sh_max, binsum, maxpow);
 }

@@ -41,72 +41,118 @@ constexpr int kRowThreads = 256;
 #define PHD_EXP_COLTHREADS 512
 #endif
 constexpr int kColThreads = PHD_EXP_COLTHREADS;
+#ifndef PHD_COLS_PACKED
+#define PHD_COLS_PACKED true  // see Cx
+#endif
+#ifndef PHD_COLS_MINB_1080
+#define PHD_COLS_MINB_1080 1
+#endif
 #ifndef PHD_COLS_GROUPS
 #define PHD_COLS_GROUPS 1  // one named-barrier thread group per column (see seq_sync)
 #endif
 
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Complex arithmetic, scalar (PK = false) or on the packed FP32x2 pipe of sm_100 (PK = true: PTX
+// add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, one instruction for both components, scalars broadcast
+// as an operand modifier).  Packed halves the instruction count of the complex adds and scalings but not their
+// time on the FP32 pipe: it pays in the column kernel, which is bound by instruction issue (-7 %), and costs a
+// little in the row kernel, which is bound by latency (+1 % at 1920, +6 % at 6000) -- so rows stay scalar.
+template <bool PK> struct Cx;
+template <> struct Cx<false> {
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+    static __device__ __forceinline__ float2 fmas(float2 a, float c, float2 b) {  // a * c + b, c real
+        return make_float2(fmaf(a.x, c, b.x), fmaf(a.y, c, b.y));
+    }
+    static __device__ __forceinline__ float2 scale(float2 a, float c) { return make_float2(a.x * c, a.y * c); }
+};
+#define PHD_PK2(op, r, a, b)                                                                                     \
+    asm("{ .reg .b64 pa, pb, pc; mov.b64 pa, {%2,%3}; mov.b64 pb, {%4,%5}; " op ".rn.f32x2 pc, pa, pb;"           \
+        " mov.b64 {%0,%1}, pc; }" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y))
+template <> struct Cx<true> {
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { float2 r; PHD_PK2("add", r, a, b); return r; }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b) { float2 r; PHD_PK2("sub", r, a, b); return r; }
+    static __device__ __forceinline__ float2 fmas(float2 a, float c, float2 b) {
+        float2 r;
+        asm("{ .reg .b64 pa, pb, pc, pd; mov.b64 pa, {%2,%3}; mov.b64 pb, {%4,%4}; mov.b64 pc, {%5,%6};"
+            " fma.rn.f32x2 pd, pa, pb, pc; mov.b64 {%0,%1}, pd; }"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(c), "f"(b.x), "f"(b.y));
+        return r;
+    }
+    static __device__ __forceinline__ float2 scale(float2 a, float c) {
+        float2 r;
+        asm("{ .reg .b64 pa, pb, pc; mov.b64 pa, {%2,%3}; mov.b64 pb, {%4,%4}; mul.rn.f32x2 pc, pa, pb;"
+            " mov.b64 {%0,%1}, pc; }" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(c));
+        return r;
+    }
+};
+// a * (c + i s): the cross terms by two scalar multiplies, the rest one (packed) FMA
+template <bool PK>
+__device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) {
+    return Cx<PK>::fmas(a, c, make_float2(-a.y * s, a.x * s));
 }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // * -i
+template <bool PK>
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return cmul_cs<PK>(a, b.x, b.y); }
+// i * (a - b) = (b.y - a.y, a.x - b.x): the rotated difference the odd outputs of a butterfly add and subtract
+__device__ __forceinline__ float2 isub(float2 a, float2 b) { return make_float2(b.y - a.y, a.x - b.x); }
 
 // ------------------------------------------------------------------------------------------
-// Register butterflies.  Radix<R>::run is an in-place R-point DFT, natural order in and out.
+// Register butterflies.  Radix<R, PK>::run is an in-place R-point DFT, natural order in and out.
 // ------------------------------------------------------------------------------------------
-template <int R> struct Radix;
+template <int R, bool PK> struct Radix;
 
-template <> struct Radix<2> {
+template <bool PK> struct Radix<2, PK> {
+    using C = Cx<PK>;
     static __device__ __forceinline__ void run(float2 (&x)[2]) {
         const float2 a = x[0], b = x[1];
-        x[0] = caddf(a, b);
-        x[1] = csubf(a, b);
+        x[0] = C::add(a, b);
+        x[1] = C::sub(a, b);
     }
 };
-template <> struct Radix<4> {
+template <bool PK> struct Radix<4, PK> {
+    using C = Cx<PK>;
     static __device__ __forceinline__ void run(float2 (&x)[4]) {
-        const float2 t0 = caddf(x[0], x[2]), t1 = csubf(x[0], x[2]);
-        const float2 t2 = caddf(x[1], x[3]), t3 = mul_mi(csubf(x[1], x[3]));
-        x[0] = caddf(t0, t2);
-        x[1] = caddf(t1, t3);
-        x[2] = csubf(t0, t2);
-        x[3] = csubf(t1, t3);
+        const float2 t0 = C::add(x[0], x[2]), t1 = C::sub(x[0], x[2]);
+        const float2 t2 = C::add(x[1], x[3]), t3 = isub(x[3], x[1]);  // -i (x1 - x3)
+        x[0] = C::add(t0, t2);
+        x[1] = C::add(t1, t3);
+        x[2] = C::sub(t0, t2);
+        x[3] = C::sub(t1, t3);
     }
 };
-template <> struct Radix<3> {
+template <bool PK> struct Radix<3, PK> {
+    using C = Cx<PK>;
     static __device__ __forceinline__ void run(float2 (&x)[3]) {
         const float k3 = 0.86602540378443864676f;
-        const float2 t = caddf(x[1], x[2]);
-        const float2 u = make_float2(x[0].x - 0.5f * t.x, x[0].y - 0.5f * t.y);
-        const float2 d = csubf(x[1], x[2]);
-        const float2 v = make_float2(k3 * d.y, -k3 * d.x);
-        x[0] = caddf(x[0], t);
-        x[1] = caddf(u, v);
-        x[2] = csubf(u, v);
+        const float2 t = C::add(x[1], x[2]);
+        const float2 u = C::fmas(t, -0.5f, x[0]);
+        const float2 v = C::scale(isub(x[2], x[1]), k3);  // -i k3 (x1 - x2)
+        x[0] = C::add(x[0], t);
+        x[1] = C::add(u, v);
+        x[2] = C::sub(u, v);
     }
 };
-template <> struct Radix<5> {
+template <bool PK> struct Radix<5, PK> {
+    using C = Cx<PK>;
     static __device__ __forceinline__ void run(float2 (&x)[5]) {
         const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
         const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-        const float2 t1 = caddf(x[1], x[4]), t2 = caddf(x[2], x[3]);
-        const float2 t3 = csubf(x[1], x[4]), t4 = csubf(x[2], x[3]);
-        const float2 m1 = make_float2(x[0].x + c1 * t1.x + c2 * t2.x, x[0].y + c1 * t1.y + c2 * t2.y);
-        const float2 m2 = make_float2(x[0].x + c2 * t1.x + c1 * t2.x, x[0].y + c2 * t1.y + c1 * t2.y);
-        const float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-        const float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-        x[0] = make_float2(x[0].x + t1.x + t2.x, x[0].y + t1.y + t2.y);
-        x[1] = make_float2(m1.x + n1.y, m1.y - n1.x);
-        x[4] = make_float2(m1.x - n1.y, m1.y + n1.x);
-        x[2] = make_float2(m2.x + n2.y, m2.y - n2.x);
-        x[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
+        const float2 t1 = C::add(x[1], x[4]), t2 = C::add(x[2], x[3]);
+        const float2 r3 = isub(x[4], x[1]), r4 = isub(x[3], x[2]);  // -i (x1 - x4), -i (x2 - x3)
+        const float2 m1 = C::fmas(t2, c2, C::fmas(t1, c1, x[0]));
+        const float2 m2 = C::fmas(t2, c1, C::fmas(t1, c2, x[0]));
+        const float2 n1 = C::fmas(r4, s2, C::scale(r3, s1));
+        const float2 n2 = C::fmas(r4, -s1, C::scale(r3, s2));
+        x[0] = C::add(C::add(x[0], t1), t2);
+        x[1] = C::add(m1, n1);
+        x[4] = C::sub(m1, n1);
+        x[2] = C::add(m2, n2);
+        x[3] = C::sub(m2, n2);
     }
 };
 
 // RA*RB-point DFT from RA- and RB-point ones (Cooley-Tukey in registers, constants folded at compile time):
 // n = n1*RB + n2, k = k1 + RA*k2;  X[k] = sum_n2 W_N^(n2 k1) [sum_n1 x[n] W_RA^(n1 k1)] W_RB^(n2 k2).
-template <int RA, int RB>
+template <int RA, int RB, bool PK>
 struct Composite {
     static __device__ __forceinline__ void run(float2 (&x)[RA * RB]) {
         constexpr int N = RA * RB;
@@ -116,15 +162,12 @@ struct Composite {
             float2 y[RA];
 #pragma unroll
             for (int n1 = 0; n1 < RA; n1++) y[n1] = x[n1 * RB + n2];
-            Radix<RA>::run(y);
+            Radix<RA, PK>::run(y);
 #pragma unroll
             for (int k1 = 0; k1 < RA; k1++) {
                 const int e = (n2 * k1) % N;
                 if (e == 0) t[n2 * RA + k1] = y[k1];
-                else {
-                    const float c = PhdTw<N>::c(e), s = PhdTw<N>::s(e);
-                    t[n2 * RA + k1] = make_float2(y[k1].x * c - y[k1].y * s, y[k1].x * s + y[k1].y * c);
-                }
+                else t[n2 * RA + k1] = cmul_cs<PK>(y[k1], PhdTw<N>::c(e), PhdTw<N>::s(e));
             }
         }
 #pragma unroll
@@ -132,7 +175,7 @@ struct Composite {
             float2 z[RB];
 #pragma unroll
             for (int n2 = 0; n2 < RB; n2++) z[n2] = t[n2 * RA + k1];
-            Radix<RB>::run(z);
+            Radix<RB, PK>::run(z);
 #pragma unroll
             for (int k2 = 0; k2 < RB; k2++) x[k1 + RA * k2] = z[k2];
         }
@@ -141,20 +184,21 @@ struct Composite {
 // Odd prime P by the definition, folded on the conjugate symmetry W^(P-k) = conj(W^k): with s_k = x[k] + x[P-k],
 // d_k = x[k] - x[P-k],  X[j] = A_j + i B_j and X[P-j] = A_j - i B_j,  A_j = x0 + sum_k cos(jk) s_k,
 // B_j = sum_k TWS(jk) d_k  ((P-1)^2 FMAs in all, constants folded at compile time).
-template <int P>
+template <int P, bool PK>
 struct PrimeRadix {
+    using C = Cx<PK>;
     static __device__ __forceinline__ void run(float2 (&x)[P]) {
         constexpr int h = (P - 1) / 2;
         float2 s[h], d[h];
 #pragma unroll
         for (int k = 1; k <= h; k++) {
-            s[k - 1] = caddf(x[k], x[P - k]);
-            d[k - 1] = csubf(x[k], x[P - k]);
+            s[k - 1] = C::add(x[k], x[P - k]);
+            d[k - 1] = isub(x[k], x[P - k]);  // i d_k, so that i B_j accumulates directly
         }
         const float2 x0 = x[0];
         float2 sum = x0;
 #pragma unroll
-        for (int k = 0; k < h; k++) sum = caddf(sum, s[k]);
+        for (int k = 0; k < h; k++) sum = C::add(sum, s[k]);
         x[0] = sum;
 #pragma unroll
         for (int j = 1; j <= h; j++) {
@@ -162,28 +206,27 @@ struct PrimeRadix {
 #pragma unroll
             for (int k = 1; k <= h; k++) {
                 const int e = (j * k) % P;
-                const float c = PhdTw<P>::c(e), t = PhdTw<P>::s(e);
-                A.x = fmaf(c, s[k - 1].x, A.x); A.y = fmaf(c, s[k - 1].y, A.y);
-                B.x = fmaf(t, d[k - 1].x, B.x); B.y = fmaf(t, d[k - 1].y, B.y);
+                A = C::fmas(s[k - 1], PhdTw<P>::c(e), A);
+                B = C::fmas(d[k - 1], PhdTw<P>::s(e), B);
             }
-            x[j] = make_float2(A.x - B.y, A.y + B.x);
-            x[P - j] = make_float2(A.x + B.y, A.y - B.x);
+            x[j] = C::add(A, B);
+            x[P - j] = C::sub(A, B);
         }
     }
 };
-template <> struct Radix<7> : PrimeRadix<7> {};
-template <> struct Radix<11> : PrimeRadix<11> {};
-template <> struct Radix<13> : PrimeRadix<13> {};
-template <> struct Radix<17> : PrimeRadix<17> {};
-template <> struct Radix<19> : PrimeRadix<19> {};
-template <> struct Radix<6> : Composite<2, 3> {};
-template <> struct Radix<8> : Composite<2, 4> {};
-template <> struct Radix<9> : Composite<3, 3> {};
-template <> struct Radix<10> : Composite<2, 5> {};
-template <> struct Radix<12> : Composite<3, 4> {};
-template <> struct Radix<15> : Composite<3, 5> {};
-template <> struct Radix<16> : Composite<4, 4> {};
-template <> struct Radix<25> : Composite<5, 5> {};
+template <bool PK> struct Radix<7, PK> : PrimeRadix<7, PK> {};
+template <bool PK> struct Radix<11, PK> : PrimeRadix<11, PK> {};
+template <bool PK> struct Radix<13, PK> : PrimeRadix<13, PK> {};
+template <bool PK> struct Radix<17, PK> : PrimeRadix<17, PK> {};
+template <bool PK> struct Radix<19, PK> : PrimeRadix<19, PK> {};
+template <bool PK> struct Radix<6, PK> : Composite<2, 3, PK> {};
+template <bool PK> struct Radix<8, PK> : Composite<2, 4, PK> {};
+template <bool PK> struct Radix<9, PK> : Composite<3, 3, PK> {};
+template <bool PK> struct Radix<10, PK> : Composite<2, 5, PK> {};
+template <bool PK> struct Radix<12, PK> : Composite<3, 4, PK> {};
+template <bool PK> struct Radix<15, PK> : Composite<3, 5, PK> {};
+template <bool PK> struct Radix<16, PK> : Composite<4, 4, PK> {};
+template <bool PK> struct Radix<25, PK> : Composite<5, 5, PK> {};
 
 // Per-pass twiddle tables of the compile-time plans: pass i (radix R, stride S, M = N/R butterflies) reads
 // twp[off_i + (j-1)*M + b] = exp(-2 pi i * (b - b % S) * j / N), j = 1..R-1 -- consecutive lanes read consecutive
@@ -212,7 +255,7 @@ __device__ __forceinline__ void seq_sync() {
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / GT), "n"(GT) : "memory");
 }
 
-template <int N, int R, int S, bool PADIN, int GT>
+template <int N, int R, int S, bool PADIN, int GT, bool PK>
 __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
                                        const float2* __restrict__ twp, int nfft, int fstride_in, int fstride_out) {
     constexpr int M = N / R;
@@ -238,14 +281,14 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
 #pragma unroll
             for (int k = 0; k < R; k++) x[k] = a[b + k * M];
         }
-        Radix<R>::run(x);
+        Radix<R, PK>::run(x);
         if (S * R == N) {  // last pass: every twiddle is 1
 #pragma unroll
             for (int j = 0; j < R; j++) y[q + j * S] = x[j];
         } else {
             y[R * pps + q] = x[0];
 #pragma unroll
-            for (int j = 1; j < R; j++) y[R * pps + q + j * S] = cmulf(x[j], __ldg(&twp[(j - 1) * M + b]));
+            for (int j = 1; j < R; j++) y[R * pps + q + j * S] = cmulf<PK>(x[j], __ldg(&twp[(j - 1) * M + b]));
         }
     }
 }
@@ -253,19 +296,19 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
 // Up to four passes; R3 == 1 means a three-pass plan.  a: input (padded layout when PADIN), b: scratch.
 // Returns the buffer holding the result (unpadded, sequences fstride apart).  The barrier after the LAST pass is
 // left to the caller (it usually needs a CTA-wide one there anyway).
-template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT>
+template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT, bool PK>
 __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ twp, int nfft,
                                              int fstride_a, int fstride) {
     static_assert(R0 * R1 * R2 * R3 == N, "radix plan does not multiply to N");
     using PL = PlanT<N, R0, R1, R2, R3>;
-    pass_t<N, R0, 1, PADIN, GT>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
+    pass_t<N, R0, 1, PADIN, GT, PK>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
     seq_sync<GT>();
-    pass_t<N, R1, R0, false, GT>(b, a, twp + PL::off1, nfft, fstride, fstride);
+    pass_t<N, R1, R0, false, GT, PK>(b, a, twp + PL::off1, nfft, fstride, fstride);
     seq_sync<GT>();
-    pass_t<N, R2, R0 * R1, false, GT>(a, b, twp + PL::off2, nfft, fstride, fstride);
+    pass_t<N, R2, R0 * R1, false, GT, PK>(a, b, twp + PL::off2, nfft, fstride, fstride);
     if (R3 == 1) return b;
     seq_sync<GT>();
-    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false, GT>(b, a, twp + PL::off3, nfft, fstride, fstride);
+    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false, GT, PK>(b, a, twp + PL::off3, nfft, fstride, fstride);
     return a;
 }
 
@@ -285,10 +328,10 @@ __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* _
         float2 x[R];
 #pragma unroll
         for (int k = 0; k < R; k++) x[k] = a[b + k * m];
-        Radix<R>::run(x);
+        Radix<R, false>::run(x);
         y[R * pps + q] = x[0];
 #pragma unroll
-        for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf(x[j], __ldg(&twp[(j - 1) * m + b]));
+        for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf<false>(x[j], __ldg(&twp[(j - 1) * m + b]));
     }
 }
 
@@ -310,9 +353,9 @@ __device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __re
             for (int k = 1; k < r; k++) {
                 e += j;
                 if (e >= r) e -= r;
-                acc = caddf(acc, cmulf(a[b + k * m], __ldg(&tw[e * m])));
+                acc = Cx<false>::add(acc, cmulf<false>(a[b + k * m], __ldg(&tw[e * m])));
             }
-            y[r * pps + q + j * s] = j ? cmulf(acc, __ldg(&twp[(j - 1) * m + b])) : acc;
+            y[r * pps + q + j * s] = j ? cmulf<false>(acc, __ldg(&twp[(j - 1) * m + b])) : acc;
         }
     }
 }
@@ -435,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
             if (q + q_step < q_end) load_step(q + q_step);
         }
         __syncthreads();  // CTA wide: the previous step's output loop (all threads read every pair's result) is over
-        const float2* z = fft_run_t<N, R0, R1, R2, R3, true, GT>(bufA, bufB, twp, PAIRS, NP, N);
+        const float2* z = fft_run_t<N, R0, R1, R2, R3, true, GT, false>(bufA, bufB, twp, PAIRS, NP, N);
         __syncthreads();  // every pair's spectrum is complete
         float2* out = specT + (size_t)img * fw * P.Hp + 2 * PAIRS * q;
         for (int k = threadIdx.x; k < fw; k += blockDim.x) {
@@ -655,8 +698,10 @@ __device__ __forceinline__ void cols_write_power(const DevParams& P, int img, in
 // bins are zeroed and flushed once per CTA, and while a group's epilogue runs the bulk-copy engine already
 // fetches the next group's columns (into the buffer the last FFT pass no longer reads) and bin-id slices.
 // Requires Hp == N (H % 4 == 0) so that columns and bin-map slices are 16-byte multiples, and a 3-pass plan.
-template <int N, int R0, int R1, int R2, int R3, int NB, bool WRITE_POWER>
-__global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float2* __restrict__ tw,
+// Two CTAs fit an SM either way.  MINB is only the register-allocation hint of __launch_bounds__ (0 = none): measured,
+// the 1080-point kernel is fastest with 1 (58 registers; 0 -> 48 and 2 -> 60 are 1-2 % slower), the longer ones with 2.
+template <int N, int R0, int R1, int R2, int R3, int NB, int MINB, bool WRITE_POWER>
+__global__ void __launch_bounds__(kColThreads, MINB) k_cols_t(DevParams P, const float2* __restrict__ tw,
                                                         const float2* __restrict__ specT,
                                                         const u16* __restrict__ binmapT,
                                                         const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
@@ -694,7 +739,7 @@ __global__ void __launch_bounds__(kColThreads) k_cols_t(DevParams P, const float
         const int it = g - g_begin;
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         mbar_wait(&bar, it & 1);
-        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT>(bufA, bufB, tw, ncol, N, N);
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT, PHD_COLS_PACKED>(bufA, bufB, tw, ncol, N, N);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (g + 1 < g_end) {
@@ -810,12 +855,12 @@ void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float
     k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS><<<dim3(gx, nimg), THREADS, smem, st>>>(rgb, P, tw, specT);
 }
 
-template <int N, int R0, int R1, int R2, int R3, int NB>
+template <int N, int R0, int R1, int R2, int R3, int NB, int MINB = 2>
 void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
                    Workspace& ws, float* power_out, cudaStream_t st) {
     const size_t smem = (size_t)2 * NB * N * sizeof(float2) + (size_t)2 * NB * N * sizeof(u16) + (size_t)2 * P.nbins * sizeof(u32);
-    PHD_ALLOW_SMEM((k_cols_t<N, R0, R1, R2, R3, NB, false>), 200 * 1024);
-    PHD_ALLOW_SMEM((k_cols_t<N, R0, R1, R2, R3, NB, true>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_cols_t<N, R0, R1, R2, R3, NB, MINB, false>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_cols_t<N, R0, R1, R2, R3, NB, MINB, true>), 200 * 1024);
     // groups per CTA: long walks amortise the bin zero/flush; pick the walk length whose CTA count fills whole
     // waves of the machine (2 CTAs of this size per SM, 148 SMs)
     const int ngroups = (P.fw + NB - 1) / NB;
@@ -830,9 +875,9 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
     }
     dim3 grid((ngroups + best - 1) / best, nimg);
     if (power_out)
-        k_cols_t<N, R0, R1, R2, R3, NB, true><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out, best);
+        k_cols_t<N, R0, R1, R2, R3, NB, MINB, true><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out, best);
     else
-        k_cols_t<N, R0, R1, R2, R3, NB, false><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr, best);
+        k_cols_t<N, R0, R1, R2, R3, NB, MINB, false><<<grid, kColThreads, smem, st>>>(P, tw, specT, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr, best);
 }
 
 }  // namespace
@@ -982,7 +1027,7 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
     *launches += 1;
     if (P.Hp == P.H) {
         switch (P.H) {
-            case 1080: launch_cols_t<1080, 9, 10, 12, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+            case 1080: launch_cols_t<1080, 9, 10, 12, 1, 4, PHD_COLS_MINB_1080>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
             case 720: launch_cols_t<720, 9, 10, 8, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;

@@ -45,6 +45,8 @@ W, H = 3840, 2160
 boxes = np.array([[[H * i // 8, H * i // 8 + H // 4, W * i // 8, W * i // 8 + W // 4] for i in range(4)]] * 128, np.int32)
 run("config2 4K + 4 boxes x128", W, H, 128, p, boxes)
 run("config4 24MP x64", 6000, 4000, 64, p)
+if "--only-big" in sys.argv:
+    sys.exit(0)
 run("config5 fine palette 1080p x256", 1920, 1080, 256, make_params(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99))
 run("config3 1080p x512", 1920, 1080, 512, p)
 if "--generic" in sys.argv:

@@ -627,8 +627,10 @@ void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, c
                              const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches) {
     const size_t smem = phd_cell_tables_bytes() + ((size_t)P.chunk + (size_t)P.ncls * P.hp) * sizeof(u16) + (size_t)P.ncls + 16;
     PHD_ALLOW_SMEM((k_palette_ties), 200 * 1024);
-    int grid = nimg * 4;
-    if (grid > 148 * 4) grid = 148 * 4;
+    // CTAs stride over the (image, chunk) work list, whose length only the device knows; CTAs beyond it retire at once.
+    // Small batches get up to 128 CTAs per image so that a single image's chunks are not walked by four CTAs.
+    long long want = (long long)nimg * (P.nchunks < 128 ? P.nchunks : 128);
+    int grid = (int)(want > 148 * 4 ? 148 * 4 : want);
     k_palette_ties<<<grid, 256, smem, st>>>(rgb, P, tabs, exc, ws.plan, ws.tie_list, ws.tie_n, ws.work, ws.work_n,
                                             ws.cells_tie);
     *launches += 1;

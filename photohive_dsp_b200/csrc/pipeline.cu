@@ -348,6 +348,63 @@ int ensure_bytes(phd_context* ctx, unsigned char** buf, size_t* have, size_t nee
     return PHD_OK;
 }
 
+// Upload of PAGEABLE host memory.  A pageable cudaMemcpy moves about 11 GB/s on this platform; here a few threads
+// copy 2 MB slices into their own pinned slices and queue the DMA on their own streams (double buffered), which is
+// bound by the host's memcpy bandwidth instead (about 4x faster).  Blocks until every byte is on the device.
+struct UploadSeg {
+    const unsigned char* src;
+    unsigned char* dst;
+    size_t bytes;
+};
+
+cudaError_t threaded_upload(phd_context* ctx, const UploadSeg* segs, int nseg) {
+    constexpr int NT = phd_context::kUpThreads;
+    constexpr size_t SL = phd_context::kUpSlice;
+    cudaError_t e = cudaSuccess;
+    if (!ctx->h_ring) e = cudaHostAlloc(&ctx->h_ring, (size_t)NT * 2 * SL, cudaHostAllocDefault);
+    for (int t = 0; t < NT && e == cudaSuccess; t++) {
+        if (!ctx->up_stream[t]) e = cudaStreamCreateWithFlags(&ctx->up_stream[t], cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; b++)
+            if (!ctx->up_ev[t][b]) e = cudaEventCreateWithFlags(&ctx->up_ev[t][b], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return e;
+    std::vector<size_t> first(nseg + 1, 0);  // first slice of every segment
+    for (int i = 0; i < nseg; i++) first[i + 1] = first[i] + (segs[i].bytes + SL - 1) / SL;
+    const size_t nslices = first[nseg];
+    if (nslices == 0) return cudaSuccess;
+    int nthreads = (int)std::min<size_t>(NT, nslices);
+    const unsigned hc = std::thread::hardware_concurrency();
+    if (hc > 0 && (unsigned)nthreads > hc) nthreads = (int)hc;
+    cudaError_t te[NT];
+    auto upload = [&](int t) {
+        cudaSetDevice(ctx->device);
+        cudaError_t err = cudaSuccess;
+        size_t mine = 0;
+        int seg = 0;
+        for (size_t sl = t; sl < nslices && err == cudaSuccess; sl += nthreads, mine++) {
+            while (sl >= first[seg + 1]) seg++;
+            const size_t off = (sl - first[seg]) * SL;
+            const size_t bytes = std::min(SL, segs[seg].bytes - off);
+            const int b = (int)(mine & 1);
+            unsigned char* stage = ctx->h_ring + ((size_t)t * 2 + b) * SL;
+            if (mine >= 2) err = cudaEventSynchronize(ctx->up_ev[t][b]);  // the slice's previous DMA is done
+            if (err != cudaSuccess) break;
+            memcpy(stage, segs[seg].src + off, bytes);
+            err = cudaMemcpyAsync(segs[seg].dst + off, stage, bytes, cudaMemcpyHostToDevice, ctx->up_stream[t]);
+            if (err == cudaSuccess) err = cudaEventRecord(ctx->up_ev[t][b], ctx->up_stream[t]);
+        }
+        if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->up_stream[t]);
+        te[t] = err;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(upload, t);
+    upload(0);
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < nthreads; t++)
+        if (te[t] != cudaSuccess) e = te[t];
+    return e;
+}
+
 bool is_device_pointer(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -355,6 +412,15 @@ bool is_device_pointer(const void* p) {
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+bool is_pageable_host_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 // Images per FFT sub-batch (the row-transformed spectra of one sub-batch live in `spec`).  Measured on B200
@@ -448,7 +514,20 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream);
         return e;
     };
-    if (!input_on_device) {
+    // pageable host input: the same double buffering, but the copy is threaded_upload, which blocks the host -- so
+    // sub-batch i+1 is uploaded AFTER the kernels of sub-batch i are queued, while they run
+    const bool pageable = !input_on_device && is_pageable_host_pointer(rgb_host_or_dev);
+    auto stage_upload = [&](int first, int slot) -> cudaError_t {
+        const int n = (n_images - first < pb) ? (n_images - first) : pb;
+        std::vector<UploadSeg> segs(n);
+        for (int i = 0; i < n; i++)
+            segs[i] = {rgb_host_or_dev + (size_t)(first + i) * image_stride, ctx->d_stage[slot] + (size_t)i * dev_stride, tight};
+        return threaded_upload(ctx, segs.data(), n);
+    };
+    if (pageable) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));  // the staging buffers are reused
+        CUDA_TRY(ctx, stage_upload(0, 0));
+    } else if (!input_on_device) {
         // order the copy stream after whatever this context did before (the staging buffers are reused)
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_consumed[0], st));
         CUDA_TRY(ctx, stage_copy(0, 0, true));
@@ -458,6 +537,7 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         const int n = (n_images - first < pb) ? (n_images - first) : pb;
         const uint8_t* d_in;
         if (input_on_device) d_in = rgb_host_or_dev + (size_t)first * image_stride;
+        else if (pageable) d_in = ctx->d_stage[batch_index & 1];
         else {
             const int slot = batch_index & 1;
             if (first + pb < n_images) CUDA_TRY(ctx, stage_copy(first + pb, slot ^ 1, batch_index >= 1));
@@ -507,6 +587,11 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         mark(&e1); span(ST_FINAL, e0, e1);
         if (!input_on_device) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_consumed[batch_index & 1], st));
         CUDA_TRY(ctx, cudaGetLastError());
+        if (pageable && first + pb < n_images) {
+            const int next_slot = (batch_index & 1) ^ 1;
+            if (batch_index >= 1) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_consumed[next_slot]));  // its reader is done
+            CUDA_TRY(ctx, stage_upload(first + pb, next_slot));
+        }
     }
     if (mark(&e_end)) return fail(ctx, PHD_E_CUDA, "cudaEventRecord failed");
     span(0, e_begin, e_end);
@@ -906,10 +991,8 @@ Full_Report_Data* get_full_report_data(Image_RGB* image, Crop_Boundaries* crop, 
         }
     }
 
-    // planes -> packed 8-bit on the device.  The planes are pageable host memory (24 B per pixel), and a pageable
-    // cudaMemcpy moves them at about 11 GB/s.  Instead, a few threads copy 2 MB slices into their own pinned slices and
-    // queue the DMA on their own streams (double buffered), which is bound by the host's memcpy bandwidth; all buffers
-    // are kept in the context between calls.
+    // planes -> packed 8-bit on the device.  The planes are pageable host memory (24 B per pixel): threaded_upload;
+    // all buffers are kept in the context between calls.
     int flag = 0;
     Full_Report_Data* result = NULL;
     const size_t stride = align_up((size_t)npx * 3, 16);
@@ -932,49 +1015,14 @@ Full_Report_Data* get_full_report_data(Image_RGB* image, Crop_Boundaries* crop, 
             if (e == cudaSuccess) ctx->d_u8_bytes = stride;
         }
         if (e == cudaSuccess && !ctx->d_flag) e = cudaMalloc(&ctx->d_flag, sizeof(int));
-        constexpr int NT = phd_context::kUpThreads;
-        constexpr size_t SL = phd_context::kUpSlice;
-        if (e == cudaSuccess && !ctx->h_ring) e = cudaHostAlloc(&ctx->h_ring, (size_t)NT * 2 * SL, cudaHostAllocDefault);
-        for (int t = 0; t < NT && e == cudaSuccess; t++) {
-            if (!ctx->up_stream[t]) e = cudaStreamCreateWithFlags(&ctx->up_stream[t], cudaStreamNonBlocking);
-            for (int b2 = 0; b2 < 2 && e == cudaSuccess; b2++)
-                if (!ctx->up_ev[t][b2]) e = cudaEventCreateWithFlags(&ctx->up_ev[t][b2], cudaEventDisableTiming);
-        }
         if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream);
         if (e == cudaSuccess) {
             const double* src[3] = {image->r, image->g, image->b};
-            const size_t per_plane = (plane_bytes + SL - 1) / SL;  // slices per plane
-            const size_t nslices = 3 * per_plane;
-            int nthreads = (int)std::min<size_t>(NT, nslices);
-            const unsigned hc = std::thread::hardware_concurrency();
-            if (hc > 0 && (unsigned)nthreads > hc) nthreads = (int)hc;
-            cudaError_t te[NT];
-            auto upload = [&](int t) {
-                cudaSetDevice(ctx->device);
-                cudaError_t err = cudaSuccess;
-                size_t mine = 0;
-                for (size_t sl = t; sl < nslices && err == cudaSuccess; sl += nthreads, mine++) {
-                    const int c = (int)(sl / per_plane);
-                    const size_t off = (sl - (size_t)c * per_plane) * SL;
-                    const size_t bytes = std::min(SL, plane_bytes - off);
-                    const int b2 = (int)(mine & 1);
-                    unsigned char* stage = ctx->h_ring + ((size_t)t * 2 + b2) * SL;
-                    if (mine >= 2) err = cudaEventSynchronize(ctx->up_ev[t][b2]);  // the slice's previous DMA is done
-                    if (err != cudaSuccess) break;
-                    memcpy(stage, reinterpret_cast<const unsigned char*>(src[c]) + off, bytes);
-                    err = cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ctx->d_planes + (size_t)c * npx) + off, stage, bytes,
-                                          cudaMemcpyHostToDevice, ctx->up_stream[t]);
-                    if (err == cudaSuccess) err = cudaEventRecord(ctx->up_ev[t][b2], ctx->up_stream[t]);
-                }
-                if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->up_stream[t]);
-                te[t] = err;
-            };
-            std::vector<std::thread> pool;
-            for (int t = 1; t < nthreads; t++) pool.emplace_back(upload, t);
-            upload(0);
-            for (auto& th : pool) th.join();
-            for (int t = 0; t < nthreads; t++)
-                if (te[t] != cudaSuccess) e = te[t];
+            UploadSeg segs[3];
+            for (int c = 0; c < 3; c++)
+                segs[c] = {reinterpret_cast<const unsigned char*>(src[c]),
+                           reinterpret_cast<unsigned char*>(ctx->d_planes + (size_t)c * npx), plane_bytes};
+            e = threaded_upload(ctx, segs, 3);
         }
         if (e == cudaSuccess) {
             k_ingest_f64<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_planes, ctx->d_planes + npx,

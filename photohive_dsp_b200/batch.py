@@ -159,7 +159,7 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # `lib` is already gone when a module-level context dies at exit
             lib.phd_context_destroy(self._h)
             self._h = None
 

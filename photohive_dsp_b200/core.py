@@ -16,12 +16,14 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from .batch import BatchReports, Context, make_params
+from .batch import BatchReports, Context, flat_layout, make_params
 from .lib import lib
 from .structures import Crop_Boundaries, Pixel_HSV
 from .utils import array_to_image_rgb, hsv_to_rgb, image_pgm_to_pillow, pil_image_to_image_rgb
 
 _VERBOSE = bool(os.environ.get("PHD_VERBOSE"))
+_VIA_DOUBLES = bool(os.environ.get("PHD_GET_REPORT_VIA_DOUBLES"))  # force the reference's C entry point in get_report
+_DEFAULT_DEVICE = int(os.environ.get("PHD_DEVICE", "0"))
 
 
 class Report:
@@ -138,17 +140,21 @@ def get_report(pil_image, salient_characters=None,
         boxes = ctypes.byref(salient_characters)
     else:
         boxes = salient_characters
-    if isinstance(pil_image, np.ndarray):
-        height, width = pil_image.shape[:2]
-        image_rgb, _keep = array_to_image_rgb(pil_image)
-    else:
-        width, height = pil_image.width, pil_image.height
-        image_rgb = pil_image_to_image_rgb(pil_image)
+    params = (h_partitions, s_partitions, v_partitions, black_thresh, gray_thresh, coverage_thresh, linked_list_size,
+              downsample_rate, radius_partitions, angle_partitions, quantity_weight, saturation_value_weight,
+              fft_streak_thresh, magnitude_thresh, blur_cutoff_ratio_denom)
     t0 = time.time()
-    ptr = lib.get_full_report_data(ctypes.byref(image_rgb), boxes, h_partitions, s_partitions, v_partitions,
-                                   black_thresh, gray_thresh, coverage_thresh, linked_list_size, downsample_rate,
-                                   radius_partitions, angle_partitions, quantity_weight, saturation_value_weight,
-                                   fft_streak_thresh, magnitude_thresh, blur_cutoff_ratio_denom)
+    ptr = None
+    if not _VIA_DOUBLES and (salient_characters is None or isinstance(salient_characters, Crop_Boundaries)):
+        ptr, height, width = _report_from_bytes(pil_image, salient_characters, params)
+    if ptr is None:
+        if isinstance(pil_image, np.ndarray):
+            height, width = pil_image.shape[:2]
+            image_rgb, _keep = array_to_image_rgb(pil_image)
+        else:
+            width, height = pil_image.width, pil_image.height
+            image_rgb = pil_image_to_image_rgb(pil_image)
+        ptr = lib.get_full_report_data(ctypes.byref(image_rgb), boxes, *params)
     if _VERBOSE:
         print(f"Elapsed time: {time.time() - t0} seconds")
     if not ptr:
@@ -159,6 +165,46 @@ def get_report(pil_image, salient_characters=None,
     report.fft_streak_threshold = fft_streak_thresh
     report.blur_cutoff_ratio_denom = blur_cutoff_ratio_denom
     return report
+
+
+def _report_from_bytes(image, crop, params):
+    """8-bit shortcut of ``get_report``: the packed bytes go to the batch entry point (n = 1) and the flat record is
+    turned into the same malloc'ed Full_Report_Data tree -- no 24 bytes per pixel of float64 planes on the way
+    (utils.py:30-46 of the reference builds them only because its C side wants doubles).  Results are identical to the
+    C entry point's (tests/test_gpu_parity.py).  Returns (None, h, w) whenever the reference's own entry point should
+    decide instead: refused sizes, boxes outside the image, an empty box list."""
+    if isinstance(image, np.ndarray):
+        arr = image
+    else:
+        arr = np.asarray(image.convert("RGB") if image.mode != "RGB" else image)
+    if arr.ndim != 3 or arr.shape[2] != 3 or arr.dtype != np.uint8:
+        return None, 0, 0
+    arr = np.ascontiguousarray(arr)
+    height, width = arr.shape[:2]
+    nb, barr = 0, None
+    if crop is not None:
+        nb = int(crop.N)
+        if nb <= 0:
+            return None, height, width
+        barr = np.array([[crop.top[i], crop.bottom[i], crop.left[i], crop.right[i]] for i in range(nb)], np.int32)
+        if (barr < 0).any() or (barr[:, :2] > height).any() or (barr[:, 2:] > width).any():
+            return None, height, width
+    ctx = _contexts.get(_DEFAULT_DEVICE)
+    if ctx is None:
+        ctx = _contexts[_DEFAULT_DEVICE] = Context(_DEFAULT_DEVICE)
+    names = ("h_partitions", "s_partitions", "v_partitions", "black_thresh", "gray_thresh", "coverage_thresh",
+             "linked_list_size", "downsample_rate", "radius_partitions", "angle_partitions", "quantity_weight",
+             "saturation_value_weight", "fft_streak_thresh", "magnitude_thresh", "blur_cutoff_ratio_denom")
+    p = make_params(**dict(zip(names, params)))
+    try:
+        lay = flat_layout(p, nb)
+        rec = np.empty((1, lay.record_bytes), np.uint8)
+        ctx.get_reports_raw(arr.ctypes.data, 1, width, height, width * height * 3, p, rec.ctypes.data,
+                            boxes_ptr=None if barr is None else barr.ctypes.data, max_boxes=nb)
+    except Exception:
+        return None, height, width  # let the C entry point print the reference's message
+    ptr = lib.phd_flat_to_full_report(rec.ctypes.data, ctypes.byref(lay))
+    return (ptr if ptr else None), height, width
 
 
 def set_bounding_boxes(bounding_boxes):

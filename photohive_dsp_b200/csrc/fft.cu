@@ -293,9 +293,11 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
     }
 }
 
-// Up to four passes; R3 == 1 means a three-pass plan.  a: input (padded layout when PADIN), b: scratch.
-// Returns the buffer holding the result (unpadded, sequences fstride apart).  The barrier after the LAST pass is
-// left to the caller (it usually needs a CTA-wide one there anyway).
+// Up to four passes; R3 == 1 means a three-pass plan.  a: input (padded layout when PADIN), b: scratch; sequence f
+// lives at a + f * fstride_a and b + f * fstride in EVERY pass -- with thread groups (GT > 0) the groups drift apart by
+// whole passes, so a sequence must never be written into another sequence's region of either buffer.
+// Returns the buffer holding the result (unpadded; stride fstride for b, fstride_a for a).  The barrier after the
+// LAST pass is left to the caller (it usually needs a CTA-wide one there anyway).
 template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT, bool PK>
 __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ twp, int nfft,
                                              int fstride_a, int fstride) {
@@ -303,12 +305,12 @@ __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2*
     using PL = PlanT<N, R0, R1, R2, R3>;
     pass_t<N, R0, 1, PADIN, GT, PK>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
     seq_sync<GT>();
-    pass_t<N, R1, R0, false, GT, PK>(b, a, twp + PL::off1, nfft, fstride, fstride);
+    pass_t<N, R1, R0, false, GT, PK>(b, a, twp + PL::off1, nfft, fstride, fstride_a);
     seq_sync<GT>();
-    pass_t<N, R2, R0 * R1, false, GT, PK>(a, b, twp + PL::off2, nfft, fstride, fstride);
+    pass_t<N, R2, R0 * R1, false, GT, PK>(a, b, twp + PL::off2, nfft, fstride_a, fstride);
     if (R3 == 1) return b;
     seq_sync<GT>();
-    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false, GT, PK>(b, a, twp + PL::off3, nfft, fstride, fstride);
+    pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false, GT, PK>(b, a, twp + PL::off3, nfft, fstride, fstride_a);
     return a;
 }
 
@@ -454,6 +456,7 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
     // its pair (2 x three 16-byte loads).  The loads of the next step are issued before the passes of this one and
     // stay in registers meanwhile.
     constexpr int SEGS = N / 16;
+    static_assert(R3 == 1, "the output loop below reads the result with stride N (buffer b)");
     constexpr int GT = THREADS / PAIRS;  // threads of one pair: they stage, transform and synchronise among themselves
     static_assert(SEGS <= GT && GT % 32 == 0, "one staging task per thread of the pair's group");
     const int pair = threadIdx.x / GT, seg = threadIdx.x % GT;

@@ -8,7 +8,7 @@ import pytest
 
 from oracle.binding import make_params as omake
 from parity import assert_report_close, boxes_array, golden_report, rel_err, report_from_batch
-from photohive_dsp_b200.batch import make_params
+from photohive_dsp_b200.batch import flat_layout, make_params
 
 pytestmark = pytest.mark.gpu
 
@@ -223,6 +223,66 @@ def test_python_get_report_surface(oracle):
     vis = rep.generate_blur_profile_image()
     assert vis.size == (320, 480)
     assert P.get_report(np.zeros((349, 350, 3), np.uint8)) is None
+
+
+def test_get_report_byte_route_equals_c_entry_point(oracle, monkeypatch):
+    """get_report sends 8-bit images to the batch entry point (no float64 planes); the report must equal the one the
+    reference's C entry point returns for the same image, field for field."""
+    import photohive_dsp_b200 as P
+    from photohive_dsp_b200 import core
+    img = oracle.generate(1, 77, 640, 480)
+    boxes = [dict(top=10, bottom=250, left=5, right=325), dict(top=100, bottom=480, left=300, right=640)]
+    for bb in (None, boxes):
+        def run():
+            return P.get_report(img, salient_characters=None if bb is None else P.set_bounding_boxes(bb))
+        monkeypatch.setattr(core, "_VIA_DOUBLES", False)
+        fast = run()
+        monkeypatch.setattr(core, "_VIA_DOUBLES", True)
+        slow = run()
+        assert fast.to_json() == slow.to_json()
+        assert fast.color_palette.colors == slow.color_palette.colors
+        assert fast.blur_profile.bins == slow.blur_profile.bins
+        assert fast.sharpnesses == slow.sharpnesses and len(fast.sharpnesses) == (0 if bb is None else 2)
+    # cases the byte route hands to the C entry point: empty box list, boxes outside the image
+    monkeypatch.setattr(core, "_VIA_DOUBLES", False)
+    rep = P.get_report(img, salient_characters=P.set_bounding_boxes([]))
+    assert rep is not None and rep.sharpnesses == []
+    assert P.get_report(img, salient_characters=P.set_bounding_boxes([dict(top=0, bottom=481, left=0, right=10)])) is None
+
+
+@pytest.mark.parametrize("W,H,n", [(800, 600, 96), (1280, 720, 48), (640, 480, 96), (1024, 768, 48), (1920, 1080, 24),
+                                   (752, 502, 24)])
+def test_records_do_not_change_from_run_to_run(ctx, oracle, W, H, n):
+    """All accumulators are integers and every shared-memory hand-over is fenced, so a batch gives the same bytes every
+    time.  (Caught a race between the row FFT's thread groups: tolerance tests alone did not see it.)"""
+    torch = pytest.importorskip("torch")
+    base = np.stack([oracle.generate(k % 3, 4000 + k, W, H) for k in range(4)])
+    imgs = torch.from_numpy(np.concatenate([base] * (n // 4))).cuda()
+    p = make_params()
+    lay = flat_layout(p, 0)
+    outs = []
+    for _ in range(4):
+        rec = np.empty((n, lay.record_bytes), np.uint8)
+        ctx.get_reports_raw(imgs.data_ptr(), n, W, H, W * H * 3, p, rec.ctypes.data)
+        outs.append(rec)
+    for rec in outs[1:]:
+        assert (rec == outs[0]).all()
+    for i in range(4, n):  # copies of one image give one record wherever they sit in the batch
+        assert (outs[0][i] == outs[0][i % 4]).all()
+
+
+def test_pageable_and_pinned_host_batches_give_identical_records(ctx, oracle):
+    """Pageable host input goes through the threaded pinned-slice uploader, pinned input through cudaMemcpy2DAsync."""
+    torch = pytest.importorskip("torch")
+    imgs = np.stack([oracle.generate(k % 3, 900 + k, 800, 600) for k in range(40)])  # > one sub-batch of 32
+    p = make_params()
+    lay = flat_layout(p, 0)
+    pinned = torch.from_numpy(imgs).pin_memory()
+    a = np.empty((40, lay.record_bytes), np.uint8)
+    b = np.empty((40, lay.record_bytes), np.uint8)
+    ctx.get_reports_raw(imgs.ctypes.data, 40, 800, 600, 800 * 600 * 3, p, a.ctypes.data)
+    ctx.get_reports_raw(pinned.data_ptr(), 40, 800, 600, 800 * 600 * 3, p, b.ctypes.data)
+    assert (a == b).all()
 
 
 def test_batch_json_export_equals_single_report_json(ctx, oracle):

@@ -80,3 +80,15 @@ run("config1 1920x1080, no boxes", 1920, 1080, None)
 W, H = 3840, 2160
 run("config2 3840x2160 + 4 boxes", W, H,
     [dict(top=H * i // 8, bottom=H * i // 8 + H // 4, left=W * i // 8, right=W * i // 8 + W // 4) for i in range(4)])
+
+# the Python front door: PIL/numpy image -> Report, through the byte route and through the reference's float64 planes
+import photohive_dsp_b200 as P  # noqa: E402
+from photohive_dsp_b200 import core  # noqa: E402
+
+img = Generator(1920, 1080, dev).batch(1).cpu().numpy()[0]
+for via in (False, True):
+    core._VIA_DOUBLES = via
+    for _ in range(2):
+        P.get_report(img)
+    m = med(lambda: P.get_report(img), 7)
+    print(f"python get_report(1080p uint8) {'via float64 planes + C entry point' if via else 'byte route'}: {m[0]:.2f} ms (min {m[1]:.2f})", flush=True)

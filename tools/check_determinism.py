@@ -11,12 +11,16 @@ dev = torch.device("cuda", 0)
 ctx = Context(0)
 p = make_params()
 lay = flat_layout(p, 0)
-def run(W, H, n, reps=6):
+def run(W, H, n, reps=6, p=p, boxes=False):
     imgs_d = Generator(W, H, dev).batch(n)
+    nb = 2 if boxes else 0
+    lay = flat_layout(p, nb)
+    barr = np.ascontiguousarray([[[0, H // 2, 0, W // 2], [H // 4, H, W // 3, W]]] * n, np.int32)
+    bkw = dict(boxes_ptr=barr.ctypes.data, max_boxes=nb) if boxes else {}
     outs = []
     for r in range(reps):
         c = np.empty((n, lay.record_bytes), np.uint8)
-        ctx.get_reports_raw(imgs_d.data_ptr(), n, W, H, W*H*3, p, c.ctypes.data)
+        ctx.get_reports_raw(imgs_d.data_ptr(), n, W, H, W*H*3, p, c.ctypes.data, **bkw)
         outs.append(c)
     bad = 0
     first_off = None
@@ -29,3 +33,10 @@ def run(W, H, n, reps=6):
     print(W, H, n, "records differing from run 0 over", reps - 1, "reruns:", bad, first_off, flush=True)
 for W, H, n in ((800, 600, 40), (800, 600, 400), (1920, 1080, 64), (1280, 720, 64), (640, 480, 64), (1024, 768, 64), (752, 502, 32)):
     run(W, H, n)
+run(3840, 2160, 16, reps=4, boxes=True)
+run(6000, 4000, 6, reps=4)
+run(4032, 3024, 4, reps=4)
+run(2560, 1440, 16, reps=4)
+run(2048, 1536, 16, reps=4)
+run(1920, 1080, 32, reps=4, p=make_params(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99))
+run(1920, 1080, 32, reps=4, p=make_params(downsample_rate=2), boxes=True)

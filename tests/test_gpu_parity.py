@@ -271,6 +271,31 @@ def test_records_do_not_change_from_run_to_run(ctx, oracle, W, H, n):
         assert (outs[0][i] == outs[0][i % 4]).all()
 
 
+def test_concurrent_callers_of_the_drop_in_entry_points(oracle):
+    """The reference is not reentrant (globals, FFTW planner); the replacement serialises callers per context instead of
+    corrupting them: four threads through get_report (both routes) get the single-threaded answers."""
+    import threading
+    import photohive_dsp_b200 as P
+    from photohive_dsp_b200 import core
+    imgs = [oracle.generate(k % 3, 600 + k, 640, 480) for k in range(4)]
+    want = [P.get_report(im).to_json() for im in imgs]
+    got = [[None] * 6 for _ in imgs]
+
+    def work(i):
+        for r in range(6):
+            core._VIA_DOUBLES = bool(r & 1)  # racy on purpose: both routes interleave across the threads
+            got[i][r] = P.get_report(imgs[i]).to_json()
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    core._VIA_DOUBLES = False
+    for i in range(4):
+        assert all(g == want[i] for g in got[i])
+
+
 def test_pageable_and_pinned_host_batches_give_identical_records(ctx, oracle):
     """Pageable host input goes through the threaded pinned-slice uploader, pinned input through cudaMemcpy2DAsync."""
     torch = pytest.importorskip("torch")
@@ -307,6 +332,21 @@ def test_non_8bit_image_is_refused_loudly(capfd):
     planes = tuple(np.full(400 * 400, 0.1234567, np.float64) for _ in range(3))
     assert not binding.call_entry_point(lib, planes, 400, 400, omake(), None)
     assert "8-bit" in capfd.readouterr().err
+
+
+@pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160), (6000, 4000), (1280, 720), (2560, 1440), (1024, 768),
+                                 (2048, 1536), (800, 600), (640, 480), (1008, 572), (752, 502)])
+def test_power_spectrum_against_float64_fft(ctx, oracle, W, H):
+    """Every compile-time FFT plan (and two runtime-radix shapes) against numpy's float64 rfft2 of the same exact gray
+    numerators, element by element: |X|^2 of the hand-written FP32 transform within 1e-4 of (value + mean level)."""
+    img = oracle.generate(0, 31 + W, W, H)
+    pw = ctx.debug_power_spectrum(img).astype(np.float64)
+    i64 = img.astype(np.int64)
+    gnum = (299 * i64[:, :, 0] + 587 * i64[:, :, 1] + 114 * i64[:, :, 2]) - 127500
+    ref = np.abs(np.fft.rfft2(gnum.astype(np.float64) / 255000.0)) ** 2
+    assert pw.shape == ref.shape
+    err = np.abs(pw - ref) / (ref + ref.mean())
+    assert err.max() < 1e-4, (W, H, float(err.max()), np.unravel_index(err.argmax(), err.shape))
 
 
 # ---- full-size, size-independent properties --------------------------------------------------------

@@ -185,6 +185,23 @@ def test_edge_images(ctx, oracle):
         assert_report_close(got, want, name)
 
 
+def test_sharpness_boxes_at_awkward_places(ctx, oracle):
+    """Crop boxes of every byte phase, touching every image edge, one pixel wide / high, and around the 126-column and
+    96-row strip sizes of the kernel, against the reference (zero padding at the CROP edge, src/filtering.c:81-107)."""
+    W, H = 701, 523  # odd width: rows start at every byte phase
+    img = oracle.generate(2, 8, W, H)
+    boxes = [dict(top=0, bottom=H, left=0, right=W), dict(top=0, bottom=1, left=0, right=W),
+             dict(top=H - 1, bottom=H, left=W - 1, right=W), dict(top=5, bottom=200, left=W - 127, right=W),
+             dict(top=H - 97, bottom=H, left=3, right=129), dict(top=17, bottom=113, left=1, right=127),
+             dict(top=17, bottom=114, left=2, right=129), dict(top=100, bottom=103, left=333, right=335),
+             dict(top=0, bottom=H, left=350, right=351), dict(top=250, bottom=H, left=0, right=253)]
+    want = oracle.report(img, omake(), boxes=boxes, nthreads=4)
+    got = report_from_batch(ctx.get_reports(img[None], boxes=boxes_array(boxes)), 0)
+    assert len(got.sharpness) == len(boxes)
+    for i, (g, w) in enumerate(zip(got.sharpness, want.sharpness)):
+        assert (np.isnan(g) and np.isnan(w)) or abs(g - w) <= 1e-9 * abs(w), (i, boxes[i], g, w)
+
+
 # ---- drop-in entry point ---------------------------------------------------------------------------
 def test_drop_in_entry_point_matches_oracle(oracle, capfd):
     """get_full_report_data on planar doubles k/255.0, exactly as core.py:442-469 calls it."""

@@ -509,27 +509,29 @@ __global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 *
     }
 }
 
-// Rows, generic (any width, runtime radix plan): a CTA walks strided row quads.  The four rows' bytes are staged into
-// shared memory (16-byte vector loads when the rows are 16-byte aligned), each thread then converts "its" pixels of
-// both row pairs to gray numerators, two packed complex sequences are transformed, and every spectrum entry of the
-// quad leaves as one 32-byte sector.  Rows past the image bottom count as gray 0.5 (a zero sequence after the bias)
-// and land in the Hp padding of the transposed spectrum.
+// Rows, generic (any width, runtime radix plan): a CTA walks strided groups of 2*NP rows (NP = 2: quads).  The rows'
+// bytes are staged into shared memory (16-byte vector loads when the rows are 16-byte aligned), each thread then
+// converts "its" pixels of the NP row pairs to gray numerators, NP packed complex sequences are transformed, and every
+// spectrum entry of the group leaves as one 32-byte sector (NP = 2) or half a sector (NP = 1: rows of 6401..12800
+// pixels, whose two pairs no longer fit shared memory).  Rows past the image bottom count as gray 0.5 (a zero sequence
+// after the bias) and land in the Hp padding of the transposed spectrum.
+template <int NP>
 __global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
                                                               float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = P.W;
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [2][W]
-    float2* bufB = bufA + 2 * W;                         // [2][W]; first holds the raw bytes of the quad (12 W <= 16 W)
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [NP][W]
+    float2* bufB = bufA + NP * W;                        // [NP][W]; first holds the raw bytes of the rows (6 W NP <= 8 W NP)
     unsigned char* raw = reinterpret_cast<unsigned char*>(bufB);
     const int img = blockIdx.y;
-    const int nquads = P.Hp / 4;
+    const int ngroups = P.Hp / (2 * NP);
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
     const int row_bytes = 3 * W;
     const bool vec = P.aligned16 != 0 && (row_bytes % 16) == 0;
-    for (int q = blockIdx.x; q < nquads; q += gridDim.x) {
-        __syncthreads();  // the previous quad's output loop has finished reading bufB
-        for (int r = 0; r < 4; r++) {
-            const int row = 4 * q + r;
+    for (int q = blockIdx.x; q < ngroups; q += gridDim.x) {
+        __syncthreads();  // the previous group's output loop has finished reading bufB
+        for (int r = 0; r < 2 * NP; r++) {
+            const int row = 2 * NP * q + r;
             unsigned char* dst = raw + (size_t)r * row_bytes;
             if (row >= P.H) continue;
             const uint8_t* src = base + (size_t)row * row_bytes;
@@ -542,32 +544,36 @@ __global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict_
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < 2 * W; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < NP * W; idx += blockDim.x) {
             const int pair = idx / W, x = idx - pair * W;
             int g[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const int row = 4 * q + 2 * pair + h;
+                const int row = 2 * NP * q + 2 * pair + h;
                 const unsigned char* px = raw + (size_t)(2 * pair + h) * row_bytes + 3 * x;
                 g[h] = row < P.H ? 299 * (int)px[0] + 587 * (int)px[1] + 114 * (int)px[2] - PHD_GRAY_BIAS : 0;
             }
             bufA[idx] = make_float2((float)g[0], (float)g[1]);
         }
         __syncthreads();
-        const float2* z = fft_run_rt(pl, bufA, bufB, 2, W);
-        float2* out = specT + (size_t)img * P.fw * P.Hp + 4 * q;
+        const float2* z = fft_run_rt(pl, bufA, bufB, NP, W);
+        float2* out = specT + (size_t)img * P.fw * P.Hp + 2 * NP * q;
         for (int k = threadIdx.x; k < P.fw; k += blockDim.x) {
             const int kc = k == 0 ? 0 : W - k;
-            float4 v[2];
+            float4 v[NP];
 #pragma unroll
-            for (int pr = 0; pr < 2; pr++) {
+            for (int pr = 0; pr < NP; pr++) {
                 const float2 zk = z[pr * W + k], zc = z[pr * W + kc];
                 v[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
             }
             float* o = reinterpret_cast<float*>(out + (size_t)k * P.Hp);
-            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(v[0].x), "f"(v[0].y),
-                         "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z), "f"(v[1].w)
-                         : "memory");
+            if (NP == 2) {
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(v[0].x), "f"(v[0].y),
+                             "f"(v[0].z), "f"(v[0].w), "f"(v[NP - 1].x), "f"(v[NP - 1].y), "f"(v[NP - 1].z), "f"(v[NP - 1].w)
+                             : "memory");
+            } else {
+                *reinterpret_cast<float4*>(o) = v[0];
+            }
         }
     }
 }
@@ -998,11 +1004,14 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
             case 640: launch_rows_t<640, 5, 8, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
         }
     }
-    const size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
+    size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
+    const bool one_pair = smem > 200 * 1024;          // rows longer than 6400 pixels: one pair per CTA
+    if (one_pair) smem /= 2;
     if (smem > 200 * 1024) return 1;
-    PHD_ALLOW_SMEM((k_rows_generic), 200 * 1024);
+    PHD_ALLOW_SMEM((k_rows_generic<1>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_rows_generic<2>), 200 * 1024);
     {
-        const int nquads = P.Hp / 4;
+        const int nquads = P.Hp / (one_pair ? 2 : 4);
         int per_sm = (int)((220 * 1024) / smem);
         if (per_sm > 8) per_sm = 8;
         if (per_sm < 1) per_sm = 1;
@@ -1011,7 +1020,8 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
         if (gx > nquads) gx = nquads;
         if (gx < 1) gx = 1;
         // one CTA per SM when four rows need more than a third of the shared memory: give it 16 warps
-        k_rows_generic<<<dim3(gx, nimg), smem > 72 * 1024 ? 512 : kRowThreads, smem, st>>>(rgb, P, row, specT);
+        if (one_pair) k_rows_generic<1><<<dim3(gx, nimg), 512, smem, st>>>(rgb, P, row, specT);
+        else k_rows_generic<2><<<dim3(gx, nimg), smem > 72 * 1024 ? 512 : kRowThreads, smem, st>>>(rgb, P, row, specT);
     }
     return 0;
 }

@@ -480,7 +480,7 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         for (int b = 0; b < 2; b++)
             if ((rc = ensure_bytes(ctx, &ctx->d_stage[b], &ctx->d_stage_bytes[b], dev_stride * pb)) != PHD_OK) return rc;
     int tc;
-    if ((size_t)P.W * 4 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
+    if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
         return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
 
     cudaStream_t st = ctx->stream;

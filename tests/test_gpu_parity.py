@@ -352,7 +352,8 @@ def test_non_8bit_image_is_refused_loudly(capfd):
 
 
 @pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160), (6000, 4000), (1280, 720), (2560, 1440), (1024, 768),
-                                 (2048, 1536), (800, 600), (640, 480), (1008, 572), (752, 502)])
+                                 (2048, 1536), (800, 600), (640, 480), (1008, 572), (752, 502),
+                                 (7680, 4320), (12800, 2560), (2600, 11000)])  # 8K; the longest row / column served
 def test_power_spectrum_against_float64_fft(ctx, oracle, W, H):
     """Every compile-time FFT plan (and two runtime-radix shapes) against numpy's float64 rfft2 of the same exact gray
     numerators, element by element: |X|^2 of the hand-written FP32 transform within 1e-4 of (value + mean level)."""
@@ -367,7 +368,7 @@ def test_power_spectrum_against_float64_fft(ctx, oracle, W, H):
 
 
 # ---- full-size, size-independent properties --------------------------------------------------------
-@pytest.mark.parametrize("W,H", [(3840, 2160), (6000, 4000)])
+@pytest.mark.parametrize("W,H", [(3840, 2160), (6000, 4000), (7680, 4320)])
 def test_full_size_properties(ctx, oracle, W, H):
     """BASELINE configs 2 and 4 (4K, 24 MP): invariants that need no CPU run of the whole pipeline."""
     img = oracle.generate(1, 2024, W, H)

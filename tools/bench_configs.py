@@ -53,3 +53,4 @@ if "--generic" in sys.argv:
     run("generic 4032x3024 x32 (runtime-radix FFT)", 4032, 3024, 32, p)
     run("generic 5472x3648 x16", 5472, 3648, 16, p)
     run("generic 1280x720 x256", 1280, 720, 256, p)
+    run("generic 7680x4320 x16 (8K, runtime-radix FFT)", 7680, 4320, 16, p)

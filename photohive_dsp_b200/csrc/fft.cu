@@ -226,6 +226,8 @@ template <bool PK> struct Radix<10, PK> : Composite<2, 5, PK> {};
 template <bool PK> struct Radix<12, PK> : Composite<3, 4, PK> {};
 template <bool PK> struct Radix<15, PK> : Composite<3, 5, PK> {};
 template <bool PK> struct Radix<16, PK> : Composite<4, 4, PK> {};
+template <bool PK> struct Radix<18, PK> : Composite<2, 9, PK> {};
+template <bool PK> struct Radix<21, PK> : Composite<3, 7, PK> {};
 template <bool PK> struct Radix<25, PK> : Composite<5, 5, PK> {};
 
 // Per-pass twiddle tables of the compile-time plans: pass i (radix R, stride S, M = N/R butterflies) reads
@@ -385,7 +387,9 @@ __device__ float2* fft_run_rt(const FftPlan& pl, float2* bufA, float2* bufB, int
             case 15: pass_rt<15>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 16: pass_rt<16>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 17: pass_rt<17>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 18: pass_rt<18>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 19: pass_rt<19>(a, b, pl.n, s, twp, nbatch, bstride); break;
+            case 21: pass_rt<21>(a, b, pl.n, s, twp, nbatch, bstride); break;
             case 25: pass_rt<25>(a, b, pl.n, s, twp, nbatch, bstride); break;
             default: pass_rt_prime(r, a, b, pl.n, s, pl.tw, twp, nbatch, bstride); break;
         }
@@ -439,8 +443,16 @@ __device__ __forceinline__ int gray16(const u32 (&w)[12], int i) {
 // despite three times the resident CTAs -- partial-sector writes are that expensive -- so every shape uses 2).
 // Requires W % 16 == 0, H % (2*PAIRS) == 0, 16-byte aligned rows.
 // ------------------------------------------------------------------------------------------
+// CTAs per SM the register allocation of the row kernel must allow: what shared memory admits, but never so many
+// that a thread is left with fewer than 64 registers (the radix-15..25 butterflies spill below that).
+constexpr int rows_min_blocks(int smem_bytes, int threads) {
+    const int by_smem = smem_bytes <= 72 * 1024 ? 3 : (smem_bytes <= 110 * 1024 ? 2 : 1);
+    const int by_regs = 65536 / (threads * 64) < 1 ? 1 : 65536 / (threads * 64);
+    return by_smem < by_regs ? by_smem : by_regs;
+}
+
 template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
-__global__ void __launch_bounds__(THREADS, (PAIRS * (2 * N + N / 16) * 8 <= 72 * 1024) ? 3 : ((PAIRS * (2 * N + N / 16) * 8 <= 110 * 1024) ? 2 : 1)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
+__global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 16) * 8, THREADS)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
                                                     const float2* __restrict__ twp, float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = N + N / 16;  // padded length
@@ -891,17 +903,23 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
 
 }  // namespace
 
-// Radix plans of the compile-time specialised lengths (must match the launch_*_t dispatch below).
+// Compile-time specialised transform lengths: X(N, R0, R1, R2, NB).  One three-pass radix plan per length serves the
+// row kernel (image width N: needs N % 16 == 0 and (N / R0) % 16 == 0) and the column kernel (image height N: needs
+// N % 8 == 0; NB = columns per CTA group).  An odd first radix keeps the stride-R0 stores of the first pass conflict
+// free.  BASELINE shapes first, then the usual video and camera sizes in both orientations (1080p, 4K, 12 / 16 / 20 /
+// 24 MP sensors at 4:3 and 3:2); any other length runs the runtime-radix kernels.
+#define PHD_FFT_PLANS(X)                                                                                           \
+    X(1920, 15, 8, 16, 2) X(3840, 15, 16, 16, 1) X(6000, 15, 25, 16, 1) X(1080, 9, 10, 12, 4) X(2160, 15, 9, 16, 2) \
+    X(4000, 25, 10, 16, 1) X(1280, 5, 16, 16, 4) X(2560, 10, 16, 16, 2) X(1024, 4, 16, 16, 4) X(2048, 8, 16, 16, 2) \
+    X(800, 5, 10, 16, 4) X(640, 5, 8, 16, 4) X(720, 9, 10, 8, 4) X(1440, 9, 10, 16, 2) X(768, 3, 16, 16, 4)        \
+    X(1536, 6, 16, 16, 2) X(600, 15, 8, 5, 4) X(480, 15, 8, 4, 4) X(960, 15, 8, 8, 4) X(1200, 15, 8, 10, 4)         \
+    X(1600, 25, 8, 8, 2) X(2448, 17, 9, 16, 2) X(3000, 15, 8, 25, 1) X(3024, 21, 12, 12, 1) X(3264, 17, 12, 16, 1)  \
+    X(3456, 18, 12, 16, 1) X(3648, 19, 12, 16, 1) X(4032, 21, 12, 16, 1) X(4608, 18, 16, 16, 1) X(5472, 19, 18, 16, 1)
+
 static bool special_radices(int n, int r[4]) {
-    static const int tab[][5] = {{1920, 15, 8, 16, 1}, {3840, 15, 16, 16, 1}, {6000, 15, 25, 16, 1},   // BASELINE rows
-                                 {1080, 9, 10, 12, 1}, {2160, 15, 9, 16, 1},  {4000, 25, 10, 16, 1},   // BASELINE columns
-                                 // common video / camera sizes (rows, then columns)
-                                 {1280, 5, 16, 16, 1}, {2560, 10, 16, 16, 1}, {1024, 4, 16, 16, 1}, {2048, 8, 16, 16, 1},
-                                 {800, 5, 10, 16, 1},  {640, 5, 8, 16, 1},
-                                 {720, 9, 10, 8, 1},   {1440, 9, 10, 16, 1},  {768, 3, 16, 16, 1},  {1536, 6, 16, 16, 1},
-                                 {600, 15, 8, 5, 1},   {480, 15, 8, 4, 1}};
-    for (const auto& t : tab)
-        if (t[0] == n) { r[0] = t[1]; r[1] = t[2]; r[2] = t[3]; r[3] = t[4]; return true; }
+#define PHD_X(N, R0, R1, R2, NB) if (n == N) { r[0] = R0; r[1] = R1; r[2] = R2; r[3] = 1; return true; }
+    PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
     return false;
 }
 
@@ -983,6 +1001,19 @@ void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st) {
     k_twiddles<<<(n + 255) / 256, 256, 0, st>>>(dev_tw, n);
 }
 
+// The row kernel stages 16 pixels per thread and pads every 16 elements: only lengths that allow it are instantiated.
+template <int N, int R0>
+constexpr bool rows_t_ok() { return N % 16 == 0 && (N / R0) % 16 == 0; }
+template <int N, int R0, int R1, int R2>
+static void launch_rows_t_if(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
+    if constexpr (rows_t_ok<N, R0>()) launch_rows_t<N, R0, R1, R2, 1, 2>(rgb, P, nimg, tw, specT, st);
+}
+template <int N, int R0, int R1, int R2, int NB>
+static void launch_cols_t_if(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
+                             Workspace& ws, float* power_out, cudaStream_t st) {
+    if constexpr (N % 8 == 0) launch_cols_t<N, R0, R1, R2, 1, NB, (N == 1080 ? PHD_COLS_MINB_1080 : 2)>(P, nimg, tw, specT, binmapT, ws, power_out, st);
+}
+
 static bool rows_fast_ok(const DevParams& P) {
     int r[4];
     return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && special_radices(P.W, r);
@@ -993,15 +1024,10 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
     *launches += 1;
     if (rows_fast_ok(P)) {
         switch (P.W) {
-            case 1920: launch_rows_t<1920, 15, 8, 16, 1, PHD_ROWS_PAIRS_1920>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 3840: launch_rows_t<3840, 15, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 6000: launch_rows_t<6000, 15, 25, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 1280: launch_rows_t<1280, 5, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 2560: launch_rows_t<2560, 10, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 1024: launch_rows_t<1024, 4, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 2048: launch_rows_t<2048, 8, 16, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 800: launch_rows_t<800, 5, 10, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
-            case 640: launch_rows_t<640, 5, 8, 16, 1, 2>(rgb, P, nimg, row.twp, specT, st); return 0;
+#define PHD_X(N, R0, R1, R2, NB) \
+    case N: if (rows_t_ok<N, R0>()) { launch_rows_t_if<N, R0, R1, R2>(rgb, P, nimg, row.twp, specT, st); return 0; } break;
+            PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
         }
     }
     size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
@@ -1040,15 +1066,10 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
     *launches += 1;
     if (P.Hp == P.H) {
         switch (P.H) {
-            case 1080: launch_cols_t<1080, 9, 10, 12, 1, 4, PHD_COLS_MINB_1080>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 2160: launch_cols_t<2160, 15, 9, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 4000: launch_cols_t<4000, 25, 10, 16, 1, 1>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 720: launch_cols_t<720, 9, 10, 8, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 1440: launch_cols_t<1440, 9, 10, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 768: launch_cols_t<768, 3, 16, 16, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 1536: launch_cols_t<1536, 6, 16, 16, 1, 2>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 600: launch_cols_t<600, 15, 8, 5, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
-            case 480: launch_cols_t<480, 15, 8, 4, 1, 4>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0;
+#define PHD_X(N, R0, R1, R2, NB) \
+    case N: if (N % 8 == 0) { launch_cols_t_if<N, R0, R1, R2, NB>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0; } break;
+            PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
         }
     }
     int tc;

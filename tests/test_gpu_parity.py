@@ -353,7 +353,11 @@ def test_non_8bit_image_is_refused_loudly(capfd):
 
 @pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160), (6000, 4000), (1280, 720), (2560, 1440), (1024, 768),
                                  (2048, 1536), (800, 600), (640, 480), (1008, 572), (752, 502),
-                                 (7680, 4320), (12800, 2560), (2600, 11000)])  # 8K; the longest row / column served
+                                 (7680, 4320), (12800, 2560), (2600, 11000),   # 8K; the longest row / column served
+                                 # camera sizes in both orientations (compile-time plans with radices 17..21)
+                                 (4032, 3024), (3024, 4032), (5472, 3648), (3648, 5472), (4000, 3000), (3000, 4000),
+                                 (3264, 2448), (2448, 3264), (4608, 3456), (3456, 4608), (1600, 1200), (1200, 1600),
+                                 (1280, 960), (960, 1280), (2160, 3840), (1080, 1920), (4000, 6000), (480, 600)])
 def test_power_spectrum_against_float64_fft(ctx, oracle, W, H):
     """Every compile-time FFT plan (and two runtime-radix shapes) against numpy's float64 rfft2 of the same exact gray
     numerators, element by element: |X|^2 of the hand-written FP32 transform within 1e-4 of (value + mean level)."""

@@ -49,8 +49,9 @@ if "--only-big" in sys.argv:
     sys.exit(0)
 run("config5 fine palette 1080p x256", 1920, 1080, 256, make_params(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99))
 run("config3 1080p x512", 1920, 1080, 512, p)
-if "--generic" in sys.argv:
-    run("generic 4032x3024 x32 (runtime-radix FFT)", 4032, 3024, 32, p)
-    run("generic 5472x3648 x16", 5472, 3648, 16, p)
-    run("generic 1280x720 x256", 1280, 720, 256, p)
-    run("generic 7680x4320 x16 (8K, runtime-radix FFT)", 7680, 4320, 16, p)
+if "--generic" in sys.argv:  # other shapes: camera sizes with compile-time plans, and the runtime-radix kernels
+    run("12 MP phone 4032x3024 x32", 4032, 3024, 32, p)
+    run("20 MP 5472x3648 x16", 5472, 3648, 16, p)
+    run("720p 1280x720 x256", 1280, 720, 256, p)
+    run("8K 7680x4320 x16 (runtime-radix FFT kernels)", 7680, 4320, 16, p)
+    run("4030x3022 x32 (runtime-radix FFT kernels, 2*5*13*31 x 2*1511)", 4030, 3022, 8, p)

@@ -40,3 +40,6 @@ run(2560, 1440, 16, reps=4)
 run(2048, 1536, 16, reps=4)
 run(1920, 1080, 32, reps=4, p=make_params(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99))
 run(1920, 1080, 32, reps=4, p=make_params(downsample_rate=2), boxes=True)
+for W, H, n in ((4032, 3024, 8), (3024, 4032, 8), (5472, 3648, 6), (3648, 5472, 6), (3264, 2448, 8), (4608, 3456, 6),
+                (1600, 1200, 16), (960, 1280, 16), (2160, 3840, 8), (4000, 6000, 4)):
+    run(W, H, n, reps=4)

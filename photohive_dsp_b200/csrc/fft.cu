@@ -21,9 +21,10 @@
 //       newton_int_sqrt src/utilities.c:43-52); image independent, built once per (W,H,nr,na) and cached.
 //
 // The *_t kernels are compile-time specialised (length and radix plan as template arguments: radix-15/16/25...
-// register butterflies with folded constants) for the shapes of BASELINE.json; every other size whose prime
-// factors are <= 1021 runs the *_generic kernels (runtime radix list 4/2/3/5 and an O(p^2) butterfly for other primes p:
-// slow for large p, but camera sizes such as 6016x4016 = (2^7*47) x (2^4*251) are served rather than refused).
+// register butterflies with folded constants) for the lengths of PHD_FFT_PLANS (BASELINE.json's shapes, video and
+// camera sizes); every other length runs the *_generic kernels (runtime radix list with register butterflies for
+// 2..13, 15..19, 21, 25 and an O(p^2) pass for any other prime p: slow for large p -- a prime side of 2011 pixels costs
+// about a millisecond per image -- but arbitrary crops are served rather than refused).
 #include <math.h>
 
 #include "fft_tables.cuh"
@@ -32,7 +33,7 @@
 namespace {
 
 #define PHD_GRAY_BIAS 127500
-#define PHD_MAX_PRIME 1021
+#define PHD_MAX_PRIME 12799  // = any side the shared-memory kernels serve; large primes are slow (O(p^2)), not refused
 constexpr int kRowThreads = 256;
 #ifndef PHD_ROWS_PAIRS_1920
 #define PHD_ROWS_PAIRS_1920 2
@@ -339,28 +340,28 @@ __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* _
     }
 }
 
-// other primes: O(r^2) butterfly straight from the definition
+// other primes (and any radix without a register butterfly): O(r^2) pass straight from the definition, one thread per
+// OUTPUT (sequence, butterfly, j) so that even a prime transform length (a single butterfly per sequence) keeps the
+// whole CTA busy; lanes of a warp share the inputs (shared-memory broadcast) and gather the twiddles from L1.
 __device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __restrict__ out, int n, int s,
                               const float2* __restrict__ tw, const float2* __restrict__ twp, int nbatch, int bstride) {
     const int m = n / r;
-    const int total = nbatch * m;
+    const int total = nbatch * m * r;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int col = idx / m;
-        const int b = idx - col * m;
+        const int rest = idx / r, j = idx - rest * r;
+        const int col = rest / m, b = rest - col * m;
         const float2* a = in + col * bstride;
         float2* y = out + col * bstride;
         const int q = b % s;
         const int pps = b - q;
-        for (int j = 0; j < r; j++) {
-            float2 acc = a[b];
-            int e = 0;  // (j * k) % r, stepped
-            for (int k = 1; k < r; k++) {
-                e += j;
-                if (e >= r) e -= r;
-                acc = Cx<false>::add(acc, cmulf<false>(a[b + k * m], __ldg(&tw[e * m])));
-            }
-            y[r * pps + q + j * s] = j ? cmulf<false>(acc, __ldg(&twp[(j - 1) * m + b])) : acc;
+        float2 acc = a[b];
+        int e = 0;  // (j * k) % r, stepped
+        for (int k = 1; k < r; k++) {
+            e += j;
+            if (e >= r) e -= r;
+            acc = Cx<false>::add(acc, cmulf<false>(a[b + k * m], __ldg(&tw[e * m])));
         }
+        y[r * pps + q + j * s] = j ? cmulf<false>(acc, __ldg(&twp[(j - 1) * m + b])) : acc;
     }
 }
 
@@ -527,11 +528,13 @@ __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 
 // spectrum entry of the group leaves as one 32-byte sector (NP = 2) or half a sector (NP = 1: rows of 6401..12800
 // pixels, whose two pairs no longer fit shared memory).  Rows past the image bottom count as gray 0.5 (a zero sequence
 // after the bias) and land in the Hp padding of the transposed spectrum.
-template <int NP>
-__global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
+// N > 0: the width is the compile-time length N with plan R0 R1 R2 (widths that have a plan but not the 16-pixel
+// granularity of k_rows_t, e.g. 1080-pixel portrait rows): same staging, compile-time passes, THREADS threads.
+template <int NP, int N = 0, int R0 = 1, int R1 = 1, int R2 = 1, int THREADS = 512>
+__global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
                                                               float2* __restrict__ specT) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int W = P.W;
+    const int W = N > 0 ? N : P.W;
     float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [NP][W]
     float2* bufB = bufA + NP * W;                        // [NP][W]; first holds the raw bytes of the rows (6 W NP <= 8 W NP)
     unsigned char* raw = reinterpret_cast<unsigned char*>(bufB);
@@ -539,7 +542,9 @@ __global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict_
     const int ngroups = P.Hp / (2 * NP);
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
     const int row_bytes = 3 * W;
-    const bool vec = P.aligned16 != 0 && (row_bytes % 16) == 0;
+    // widest load every row start allows: 16 bytes, else 8 (e.g. 1080-pixel rows), else 4, else single bytes
+    const int gran = (int)((reinterpret_cast<uintptr_t>(base) | (uintptr_t)row_bytes) & 15);
+    const int vw = gran == 0 ? 16 : ((gran & 7) == 0 ? 8 : ((gran & 3) == 0 ? 4 : 1));
     for (int q = blockIdx.x; q < ngroups; q += gridDim.x) {
         __syncthreads();  // the previous group's output loop has finished reading bufB
         for (int r = 0; r < 2 * NP; r++) {
@@ -547,10 +552,18 @@ __global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict_
             unsigned char* dst = raw + (size_t)r * row_bytes;
             if (row >= P.H) continue;
             const uint8_t* src = base + (size_t)row * row_bytes;
-            if (vec) {
+            if (vw == 16) {
                 const uint4* s4 = reinterpret_cast<const uint4*>(src);
                 uint4* d4 = reinterpret_cast<uint4*>(dst);
                 for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+            } else if (vw == 8) {
+                const uint2* s2 = reinterpret_cast<const uint2*>(src);
+                uint2* d2 = reinterpret_cast<uint2*>(dst);
+                for (int i = threadIdx.x; i < row_bytes / 8; i += blockDim.x) d2[i] = __ldg(s2 + i);
+            } else if (vw == 4) {
+                const u32* s1 = reinterpret_cast<const u32*>(src);
+                u32* d1 = reinterpret_cast<u32*>(dst);
+                for (int i = threadIdx.x; i < row_bytes / 4; i += blockDim.x) d1[i] = __ldg(s1 + i);
             } else {
                 for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) dst[i] = __ldg(src + i);
             }
@@ -568,7 +581,13 @@ __global__ void __launch_bounds__(512) k_rows_generic(const uint8_t* __restrict_
             bufA[idx] = make_float2((float)g[0], (float)g[1]);
         }
         __syncthreads();
-        const float2* z = fft_run_rt(pl, bufA, bufB, NP, W);
+        const float2* z;
+        if constexpr (N > 0) {
+            z = fft_run_t<N, R0, R1, R2, 1, false, THREADS / NP, false>(bufA, bufB, pl.twp, NP, N, N);
+            __syncthreads();
+        } else {
+            z = fft_run_rt(pl, bufA, bufB, NP, W);
+        }
         float2* out = specT + (size_t)img * P.fw * P.Hp + 2 * NP * q;
         for (int k = threadIdx.x; k < P.fw; k += blockDim.x) {
             const int kc = k == 0 ? 0 : W - k;
@@ -1014,6 +1033,27 @@ static void launch_cols_t_if(const DevParams& P, int nimg, const float2* tw, con
     if constexpr (N % 8 == 0) launch_cols_t<N, R0, R1, R2, 1, NB, (N == 1080 ? PHD_COLS_MINB_1080 : 2)>(P, nimg, tw, specT, binmapT, ws, power_out, st);
 }
 
+static int rows_generic_grid(size_t smem, int ngroups, int nimg) {
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (long long)per_sm * 148 * 4;
+    int gx = (int)((want + nimg - 1) / nimg);
+    if (gx > ngroups) gx = ngroups;
+    return gx < 1 ? 1 : gx;
+}
+// Lengths with a plan that k_rows_t cannot take (1080, 3000, 600): staged bytes + compile-time passes.
+template <int N, int R0, int R1, int R2>
+static void launch_rows_staged_if(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* specT,
+                                  cudaStream_t st) {
+    if constexpr (!rows_t_ok<N, R0>()) {
+        constexpr int TH = N <= 2048 ? 256 : 512;
+        const size_t smem = (size_t)N * 4 * sizeof(float2);
+        PHD_ALLOW_SMEM((k_rows_generic<2, N, R0, R1, R2, TH>), 200 * 1024);
+        k_rows_generic<2, N, R0, R1, R2, TH><<<dim3(rows_generic_grid(smem, P.Hp / 4, nimg), nimg), TH, smem, st>>>(rgb, P, row, specT);
+    }
+}
+
 static bool rows_fast_ok(const DevParams& P) {
     int r[4];
     return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && special_radices(P.W, r);
@@ -1030,6 +1070,12 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
 #undef PHD_X
         }
     }
+    switch (P.W) {
+#define PHD_X(N, R0, R1, R2, NB) \
+    case N: if (!rows_t_ok<N, R0>()) { launch_rows_staged_if<N, R0, R1, R2>(rgb, P, nimg, row, specT, st); return 0; } break;
+        PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
+    }
     size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
     const bool one_pair = smem > 200 * 1024;          // rows longer than 6400 pixels: one pair per CTA
     if (one_pair) smem /= 2;
@@ -1037,14 +1083,7 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
     PHD_ALLOW_SMEM((k_rows_generic<1>), 200 * 1024);
     PHD_ALLOW_SMEM((k_rows_generic<2>), 200 * 1024);
     {
-        const int nquads = P.Hp / (one_pair ? 2 : 4);
-        int per_sm = (int)((220 * 1024) / smem);
-        if (per_sm > 8) per_sm = 8;
-        if (per_sm < 1) per_sm = 1;
-        long long want = (long long)per_sm * 148 * 4;
-        int gx = (int)((want + nimg - 1) / nimg);
-        if (gx > nquads) gx = nquads;
-        if (gx < 1) gx = 1;
+        const int gx = rows_generic_grid(smem, P.Hp / (one_pair ? 2 : 4), nimg);
         // one CTA per SM when four rows need more than a third of the shared memory: give it 16 warps
         if (one_pair) k_rows_generic<1><<<dim3(gx, nimg), 512, smem, st>>>(rgb, P, row, specT);
         else k_rows_generic<2><<<dim3(gx, nimg), smem > 72 * 1024 ? 512 : kRowThreads, smem, st>>>(rgb, P, row, specT);

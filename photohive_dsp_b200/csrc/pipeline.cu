@@ -264,7 +264,7 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
     s.W = W; s.H = H; s.nr = nr; s.na = na;
     s.row.n = W; s.col.n = H;
     if (phd_fft_plan_factors(W, s.row.fac, &s.row.nfac) || phd_fft_plan_factors(H, s.col.fac, &s.col.nfac))
-        return fail(ctx, PHD_E_UNSUPPORTED, "image side has a prime factor > 1021: FFT length not supported by this build");
+        return fail(ctx, PHD_E_UNSUPPORTED, "image side has too many or too large prime factors: FFT length not supported by this build");
     const int Hp = (H + 3) / 4 * 4;
     const size_t nspec = (size_t)(W / 2 + 1) * Hp;
     const size_t pe_row = phd_fft_pass_table_entries(s.row), pe_col = phd_fft_pass_table_entries(s.col);

@@ -31,19 +31,9 @@ def test_group_id_of_all_2pow24_colours(ctx, oracle, kw):
 @pytest.mark.parametrize("shape", [(1920, 1080), (3840, 2160), (6000, 4000), (405, 357), (1080, 1920), (350, 350), (752, 502)])
 def test_polar_bin_map_is_identical(ctx, oracle, shape):
     """bin ids (truncated PI, Newton sqrt, bottom-half row rule) and bin populations."""
-    assert all(_largest_prime(s) <= 1021 for s in shape)  # lengths this build's radix set covers
     m, c = ctx.debug_bin_map(*shape)
     mo, co = oracle.bin_map(*shape)
     assert np.array_equal(m, mo) and np.array_equal(c, co)
-
-
-def _largest_prime(n):
-    best, p = 1, 2
-    while p * p <= n:
-        while n % p == 0:
-            best, n = p, n // p
-        p += 1
-    return max(best, n) if n > 1 else best
 
 
 @pytest.mark.parametrize("kind,kw", [(0, {}), (1, {}), (1, dict(downsample_rate=3)), (0, FINE)])
@@ -75,6 +65,7 @@ def test_report_matches_reference_golden(ctx, oracle, golden, name):
     (752, 502, 1, {}),     # 2^4*47 x 2*251: prime factors served by the O(p^2) butterfly of the generic FFT kernels
     (1008, 572, 0, {}),    # 2^4*3^2*7 x 2^2*11*13: register butterflies for the primes 7, 11 and 13
     (646, 456, 1, {}),     # 2*17*19 x 2^3*3*19
+    (1031, 523, 2, {}),    # both sides prime (1031 > the 1021 that earlier builds refused)
     # saliencies closer than 1 apart: the truncating comparator calls them equal (insertion-sort replay)
     (800, 600, 0, dict(quantity_weight=0.0, saturation_value_weight=1e-5)),
     (800, 600, 1, dict(quantity_weight=1e-6, saturation_value_weight=1e-6, coverage_thresh=0.5)),
@@ -357,7 +348,8 @@ def test_non_8bit_image_is_refused_loudly(capfd):
                                  # camera sizes in both orientations (compile-time plans with radices 17..21)
                                  (4032, 3024), (3024, 4032), (5472, 3648), (3648, 5472), (4000, 3000), (3000, 4000),
                                  (3264, 2448), (2448, 3264), (4608, 3456), (3456, 4608), (1600, 1200), (1200, 1600),
-                                 (1280, 960), (960, 1280), (2160, 3840), (1080, 1920), (4000, 6000), (480, 600)])
+                                 (1280, 960), (960, 1280), (2160, 3840), (1080, 1920), (4000, 6000), (480, 600), (600, 480),
+                                 (2011, 1511), (1511, 2011), (4030, 3020), (1031, 523)])  # prime sides: the O(p^2) pass
 def test_power_spectrum_against_float64_fft(ctx, oracle, W, H):
     """Every compile-time FFT plan (and two runtime-radix shapes) against numpy's float64 rfft2 of the same exact gray
     numerators, element by element: |X|^2 of the hand-written FP32 transform within 1e-4 of (value + mean level)."""

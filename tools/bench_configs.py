@@ -53,5 +53,7 @@ if "--generic" in sys.argv:  # other shapes: camera sizes with compile-time plan
     run("12 MP phone 4032x3024 x32", 4032, 3024, 32, p)
     run("20 MP 5472x3648 x16", 5472, 3648, 16, p)
     run("720p 1280x720 x256", 1280, 720, 256, p)
+    run("portrait 1080x1920 x256 (rows: runtime-radix kernel, width not a multiple of 16)", 1080, 1920, 256, p)
+    run("portrait 3024x4032 x32", 3024, 4032, 32, p)
     run("8K 7680x4320 x16 (runtime-radix FFT kernels)", 7680, 4320, 16, p)
-    run("4030x3022 x32 (runtime-radix FFT kernels, 2*5*13*31 x 2*1511)", 4030, 3022, 8, p)
+    run("4030x3020 x8 (runtime-radix FFT kernels, 2*5*13*31 x 4*5*151)", 4030, 3020, 8, p)

@@ -35,22 +35,9 @@ namespace {
 #define PHD_GRAY_BIAS 127500
 #define PHD_MAX_PRIME 12799  // = any side the shared-memory kernels serve; large primes are slow (O(p^2)), not refused
 constexpr int kRowThreads = 256;
-#ifndef PHD_ROWS_PAIRS_1920
-#define PHD_ROWS_PAIRS_1920 2
-#endif
-#ifndef PHD_EXP_COLTHREADS
-#define PHD_EXP_COLTHREADS 512
-#endif
-constexpr int kColThreads = PHD_EXP_COLTHREADS;
-#ifndef PHD_COLS_PACKED
-#define PHD_COLS_PACKED true  // see Cx
-#endif
-#ifndef PHD_COLS_MINB_1080
-#define PHD_COLS_MINB_1080 1
-#endif
-#ifndef PHD_COLS_GROUPS
-#define PHD_COLS_GROUPS 1  // one named-barrier thread group per column (see seq_sync)
-#endif
+constexpr int kColThreads = 512;
+constexpr bool kColsPacked = true;  // column butterflies on the FP32x2 pipe (see Cx)
+constexpr int kColsMinBlocks1080 = 1; // register hint of the 1080-point column kernel (see k_cols_t)
 
 // Complex arithmetic, scalar (PK = false) or on the packed FP32x2 pipe of sm_100 (PK = true: PTX
 // add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, one instruction for both components, scalars broadcast
@@ -421,10 +408,6 @@ __global__ void k_pass_twiddles(float2* out, int n, int r, int s) {
     out[i] = make_float2((float)cs, (float)(-sn));
 }
 
-__device__ __forceinline__ int gray_num(const uint8_t* __restrict__ p) {
-    return 299 * (int)__ldg(p) + 587 * (int)__ldg(p + 1) + 114 * (int)__ldg(p + 2);
-}
-
 // Gray numerator 299 R + 587 G + 114 B - 127500 of pixel i (0..15) of 48 packed bytes: two 2-way dot products
 // (16-bit weights x bytes, IDP.2A) straight on the packed words, whatever the pixel's byte alignment.
 __device__ __forceinline__ int gray16(const u32 (&w)[12], int i) {
@@ -455,7 +438,7 @@ constexpr int rows_min_blocks(int smem_bytes, int threads) {
 template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 16) * 8, THREADS)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
                                                     const float2* __restrict__ twp, float2* __restrict__ specT) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = N + N / 16;  // padded length
     float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [PAIRS][NP]  (also pass scratch: [PAIRS][N] fits)
     float2* bufB = bufA + PAIRS * NP;                    // [PAIRS][N]
@@ -533,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 
 template <int NP, int N = 0, int R0 = 1, int R1 = 1, int R2 = 1, int THREADS = 512>
 __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
                                                               float2* __restrict__ specT) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = N > 0 ? N : P.W;
     float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [NP][W]
     float2* bufB = bufA + NP * W;                        // [NP][W]; first holds the raw bytes of the rows (6 W NP <= 8 W NP)
@@ -747,7 +730,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_cols_t(DevParams P, const
                                                         const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
                                                         u32* __restrict__ maxpow, float* __restrict__ power_out, int gpc) {
     static_assert(R3 == 1, "the prefetch below assumes the result lands in bufB");
-    constexpr int GT = PHD_COLS_GROUPS ? kColThreads / NB : 0;  // thread group of one column (see seq_sync)
+    constexpr int GT = kColThreads / NB;  // thread group of one column (see seq_sync)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + NB * N;
@@ -779,7 +762,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_cols_t(DevParams P, const
         const int it = g - g_begin;
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         mbar_wait(&bar, it & 1);
-        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT, PHD_COLS_PACKED>(bufA, bufB, tw, ncol, N, N);
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT, kColsPacked>(bufA, bufB, tw, ncol, N, N);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (g + 1 < g_end) {
@@ -811,7 +794,7 @@ __global__ void __launch_bounds__(kColThreads, 2) k_cols_generic(DevParams P, Ff
                                                               const ImageAcc* __restrict__ iacc,
                                                               u64* __restrict__ binsum, u32* __restrict__ maxpow,
                                                               float* __restrict__ power_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Hp = P.Hp;
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + (size_t)TC * Hp;
@@ -885,10 +868,7 @@ void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float
     if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
     if (per_sm < 1) per_sm = 1;
     const int nsteps = P.H / (2 * PAIRS);
-#ifndef PHD_EXP_ROWWAVES
-#define PHD_EXP_ROWWAVES 4
-#endif
-    long long want = (long long)per_sm * 148 * PHD_EXP_ROWWAVES;
+    long long want = (long long)per_sm * 148 * 4;
     int gx = (int)((want + nimg - 1) / nimg);
     if (gx > nsteps) gx = nsteps;
     if (gx < 1) gx = 1;
@@ -1030,7 +1010,7 @@ static void launch_rows_t_if(const uint8_t* rgb, const DevParams& P, int nimg, c
 template <int N, int R0, int R1, int R2, int NB>
 static void launch_cols_t_if(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
                              Workspace& ws, float* power_out, cudaStream_t st) {
-    if constexpr (N % 8 == 0) launch_cols_t<N, R0, R1, R2, 1, NB, (N == 1080 ? PHD_COLS_MINB_1080 : 2)>(P, nimg, tw, specT, binmapT, ws, power_out, st);
+    if constexpr (N % 8 == 0) launch_cols_t<N, R0, R1, R2, 1, NB, (N == 1080 ? kColsMinBlocks1080 : 2)>(P, nimg, tw, specT, binmapT, ws, power_out, st);
 }
 
 static int rows_generic_grid(size_t smem, int ngroups, int nimg) {

@@ -19,10 +19,7 @@
 
 namespace {
 
-#ifndef PHD_EXP_UNROLL
-#define PHD_EXP_UNROLL 15  // the 15 pixels after the first: fully unrolled
-#endif
-constexpr int kPixUnroll = PHD_EXP_UNROLL;
+constexpr int kPixUnroll = 15;  // the 15 pixels after the first: fully unrolled (partial unrolling measured slower)
 
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
@@ -601,10 +598,7 @@ void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const u
     // chunks per CTA: long walks amortise the table load and the final flush; enough CTAs to fill 148 SMs
     long long total = (long long)P.nchunks * nimg;
     int cpp = (int)(total / (148 * 12));
-#ifndef PHD_EXP_CPPCAP
-#define PHD_EXP_CPPCAP 32
-#endif
-    cpp = cpp < 1 ? 1 : (cpp > PHD_EXP_CPPCAP ? PHD_EXP_CPPCAP : cpp);
+    cpp = cpp < 1 ? 1 : (cpp > 32 ? 32 : cpp);
     dim3 grid((P.nchunks + cpp - 1) / cpp, nimg);
     const bool ds = P.ds > 1;
     if (P.fe_threads == 256) {

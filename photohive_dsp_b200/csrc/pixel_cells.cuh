@@ -96,12 +96,7 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
     const bool isR = (R == mx), isG = (G == mx);
     const int p = isR ? (G - B) : (isG ? (B - R) : (R - G));
     const float offk = isR ? 0.0f : (isG ? 240.0f : 480.0f);
-#ifdef PHD_EXP_MAGICI2F
-    const float pf = __uint_as_float(PHD_MAGIC_RN_BITS + (u32)p) - PHD_MAGIC_RN;
-    const float qf = __uint_as_float(PHD_MAGIC_FLOOR_BITS | (u32)q) - PHD_MAGIC_FLOOR;
-#else
     const float pf = (float)p, qf = (float)q;
-#endif
     float num2 = fmaf(120.0f, pf, offk * qf);          // 120 * (off*q + p), exact
     if (num2 < 0.0f) num2 = fmaf(720.0f, qf, num2);    // h < 0 -> h + 360 (:398-404)
     const int cls = svtab[((mx * mx + mx) >> 1) + mn];
@@ -125,13 +120,9 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
         hbits = PHD_MAGIC_RN_BITS + (code >> 7) * K.full_val;
     }
     // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
-#ifndef PHD_EXP_NO_SATCLAMP
+    // (delta == max gives 2^QS, the clamp turns it into 0.999999; max == 0 gives 0 through the fmax)
     const u32 sraw = __float_as_uint(fmaf(qf * phd_rcp(fmaxf((float)mx, 1.0f)), K.qscale, PHD_MAGIC_RN));
     const u32 sbits = min(sraw, K.sat1_bits);
-#else
-    u32 sbits = __float_as_uint(fmaf(qf * phd_rcp((float)mx), K.qscale, PHD_MAGIC_RN));
-    if (mn == 0) sbits = (mx == 0) ? PHD_MAGIC_RN_BITS : K.sat1_bits;
-#endif
     o.cell = cell;
     o.w0 = (mx == 255) ? 0x10001u : 1u;
     o.mx = (u32)mx;

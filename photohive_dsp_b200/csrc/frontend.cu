@@ -67,10 +67,18 @@ struct CellRun {
     u32 w0, mx, s, h;
 };
 
-// STRIDE_B > 0: compile-time byte stride between the four word arrays (immediate offsets); 0: runtime stride.
-template <int STRIDE_B>
+// STRIDE_B > 0: compile-time byte stride between the word arrays (immediate offsets); 0: runtime stride.
+// NW = 4: words w0, mx, s, h.  NW = 3: word 0 is (count << 20 | sum max) and travels in r.mx; r.w0 is unused.
+template <int STRIDE_B, int NW>
 __device__ __forceinline__ void run_emit(u32 addr, const CellRun& r, u32 stride_b) {
-    if (STRIDE_B > 0) {
+    if (NW == 3) {
+        static_assert(NW == 4 || STRIDE_B > 0, "the three-word layout has a compile-time stride");
+        asm volatile(
+            "red.shared.add.u32 [%0], %1;\n\t"
+            "red.shared.add.u32 [%0+%4], %2;\n\t"
+            "red.shared.add.u32 [%0+%5], %3;"
+            ::"r"(addr), "r"(r.mx), "r"(r.s), "r"(r.h), "n"(STRIDE_B), "n"(2 * STRIDE_B));
+    } else if (STRIDE_B > 0) {
         asm volatile(
             "red.shared.add.u32 [%0], %1;\n\t"
             "red.shared.add.u32 [%0+%5], %2;\n\t"
@@ -88,13 +96,25 @@ __device__ __forceinline__ void run_emit(u32 addr, const CellRun& r, u32 stride_
     }
 }
 
-template <int STRIDE_B>
+// word 0 of the three-word layout: one pixel and its max
+__device__ __forceinline__ u32 phd_w3_word0(const PixOut& o) { return o.mx | (1u << 20); }
+
+template <int STRIDE_B, int NW>
+__device__ __forceinline__ void run_start(CellRun& r, u32 base, const PixOut& o) {
+    r.addr = base + 4u * (u32)o.cell;
+    r.w0 = o.w0;
+    r.mx = NW == 3 ? phd_w3_word0(o) : o.mx;
+    r.s = o.sbits;
+    r.h = o.hbits;
+}
+
+template <int STRIDE_B, int NW>
 __device__ __forceinline__ void run_step(CellRun& r, u32 base, u32 scratch, u32 stride_b, const PixOut& o) {
     const u32 addr = base + 4u * (u32)o.cell;
     const bool change = (addr != r.addr);
-    run_emit<STRIDE_B>(change ? r.addr : scratch, r, stride_b);
-    r.w0 = (change ? 0u : r.w0) + o.w0;
-    r.mx = (change ? 0u : r.mx) + o.mx;
+    run_emit<STRIDE_B, NW>(change ? r.addr : scratch, r, stride_b);
+    if (NW == 4) r.w0 = (change ? 0u : r.w0) + o.w0;
+    r.mx = (change ? 0u : r.mx) + (NW == 3 ? phd_w3_word0(o) : o.mx);
     r.s = (change ? 0u : r.s) + o.sbits;
     r.h = (change ? 0u : r.h) + o.hbits;
     r.addr = addr;
@@ -127,12 +147,20 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     constexpr int CHUNK = THREADS * 16;
     constexpr int QS = (THREADS == 256) ? 20 : 19;
     static_assert(THREADS == 256 || THREADS == 512, "chunk size / QS pairs");
+    // Three chunk words per cell instead of four (the kernel is bound by the shared-memory atomics): count and sum of
+    // max share word 0 (count << 20 | sum max: 4096 pixels * 255 < 2^20), and the pixels with max == 255 -- whose count
+    // the v clamp needs -- go to TWIN cells behind the ordinary ones (the twin class ids come straight out of a
+    // second class table, so the pixel loop pays nothing) and are folded into their base cells by the drain.
+    constexpr bool W3 = (THREADS == 256);
+    constexpr int NW = W3 ? 3 : 4;
+    static_assert(!W3 || (NCS > 0 && DB), "the three-word layout is the double-buffered fixed-stride variant");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NC = P.NC;
+    const int NCW = W3 ? NC + (P.sp + 1) * P.hp * 4 : NC;  // cells of the chunk arrays: ordinary + twins
     const int ncs = NCS > 0 ? NCS : NC + 32;  // word stride of the chunk arrays (cells + 32 scratch cells)
     unsigned char* tb_raw = smem_raw;
-    u32* chunkW = reinterpret_cast<u32*>(smem_raw + phd_cell_tables_bytes());      // [DB ? 2 : 1][4][ncs]
-    u64* acc_s = reinterpret_cast<u64*>(chunkW + (DB ? 8 : 4) * ncs);              // [NC]
+    u32* chunkW = reinterpret_cast<u32*>(smem_raw + phd_cell_tables_bytes());      // [DB ? 2 : 1][NW][ncs]
+    u64* acc_s = reinterpret_cast<u64*>(chunkW + (DB ? 2 : 1) * NW * ncs);         // [NC]
     u64* acc_h = acc_s + NC;                                                       // [NC]
     u32* acc_cnt = reinterpret_cast<u32*>(acc_h + NC);                             // [NC]
     u32* acc_n255 = acc_cnt + NC;
@@ -142,8 +170,8 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
 
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
-    phd_cell_tabs_to_smem(tb_raw, tabs_g);
-    for (int i = tid; i < (DB ? 8 : 4) * ncs; i += THREADS) chunkW[i] = 0;
+    phd_cell_tabs_to_smem(tb_raw, tabs_g + (W3 ? phd_cell_tables_bytes() : 0));  // W3: the table with the twin classes
+    for (int i = tid; i < (DB ? 2 : 1) * NW * ncs; i += THREADS) chunkW[i] = 0;
     for (int i = tid; i < NC; i += THREADS) {
         acc_s[i] = 0; acc_h[i] = 0; acc_cnt[i] = 0; acc_n255[i] = 0; acc_mx[i] = 0;
     }
@@ -152,6 +180,9 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     const unsigned char* svtab = tb_raw;
     const CellCfg K = phd_cell_cfg(P, QS);
     const int spvp = P.sp * P.vp, hp = P.hp, npairs_colour = spvp * hp;
+    const int twin_pair0 = NC / 4;                  // first twin pair of the chunk arrays
+    const int black_cell = (spvp + 1) * hp * 4 + 1; // cell of the colour (0,0,0)
+    int saw = 0;                                    // this thread's last drain met a non-empty cell
     {   // keep the table pointer in registers: the compiler would reload it from the constant bank per pixel
         unsigned long long e;
         asm volatile("mov.u64 %0, %1;" : "=l"(e) : "l"(exc));
@@ -159,7 +190,7 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     }
     const u32 cw_base0 = (u32)__cvta_generic_to_shared(chunkW);
     const u32 stride_b = 4u * (u32)ncs;
-    const u32 set_b = 4u * stride_b;  // bytes between the two chunk sets
+    const u32 set_b = (u32)NW * stride_b;  // bytes between the two chunk sets
 
     u32 sum[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
     const int c_begin = blockIdx.x * cpp, c_end = min(c_begin + cpp, P.nchunks);
@@ -172,7 +203,7 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     for (int chunk = c_begin; chunk < c_end; chunk++) {
         const int set = DB ? ((chunk - c_begin) & 1) : 0;
         const u32 cw_base = cw_base0 + (u32)set * set_b;
-        const u32 scratch = cw_base + 4u * (u32)(NC + lane);
+        const u32 scratch = cw_base + 4u * (u32)(NCW + lane);
         const long long p0 = (long long)chunk * CHUNK + (long long)tid * 16;
         if (fast_ok && p0 + 16 <= P.hpx) {
             u32 wn[12];
@@ -183,14 +214,14 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
             CellRun run;
             {
                 const PixOut o = phd_pixel(packed_byte(w, 0), packed_byte(w, 1), packed_byte(w, 2), svtab, K, exc);
-                run.addr = cw_base + 4u * (u32)o.cell; run.w0 = o.w0; run.mx = o.mx; run.s = o.sbits; run.h = o.hbits;
+                run_start<4 * NCS, NW>(run, cw_base, o);
             }
 #pragma unroll kPixUnroll
             for (int i = 1; i < 16; i++)
-                run_step<4 * NCS>(run, cw_base, scratch, stride_b,
+                run_step<4 * NCS, NW>(run, cw_base, scratch, stride_b,
                                   phd_pixel(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1), packed_byte(w, 3 * i + 2),
                                             svtab, K, exc));
-            run_emit<4 * NCS>(run.addr, run, stride_b);
+            run_emit<4 * NCS, NW>(run.addr, run, stride_b);
             if (more) {
 #pragma unroll
                 for (int i = 0; i < 12; i++) w[i] = wn[i];
@@ -210,24 +241,60 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
                 }
                 const PixOut o = phd_pixel(R, G, B, svtab, K, exc);
                 if (!any) {
-                    run.addr = cw_base + 4u * (u32)o.cell; run.w0 = o.w0; run.mx = o.mx; run.s = o.sbits; run.h = o.hbits;
+                    run_start<4 * NCS, NW>(run, cw_base, o);
                     any = true;
                 } else {
-                    run_step<4 * NCS>(run, cw_base, scratch, stride_b, o);
+                    run_step<4 * NCS, NW>(run, cw_base, scratch, stride_b, o);
                 }
             }
-            if (any) run_emit<4 * NCS>(run.addr, run, stride_b);
+            if (any) run_emit<4 * NCS, NW>(run.addr, run, stride_b);
         }
-        __syncthreads();  // the only barrier of the chunk: set `set` is complete, the other set is free again
+        // the only barrier of the chunk: set `set` is complete, the other set is free again.  W3: it also tells whether
+        // the previous chunk's drain met any non-empty cell -- a chunk of 4096 pure black pixels wraps word 0 of its
+        // one cell to zero (count 4096 << 20, sum max 0, s = h = 0) and looks empty; every other full cell is caught by
+        // its non-zero sum max (see drain3)
+        const int any_prev = W3 ? __syncthreads_or(saw) : (__syncthreads(), 1);
+        saw = 0;
         // drain: chunk words -> running sums, per-chunk group counts (needed for raster ranks in the tie path)
-        u32* cw = chunkW + (size_t)set * 4 * ncs;
+        u32* cw = chunkW + (size_t)set * NW * ncs;
         u16* cc = counts_chunk + ((size_t)img * P.nchunks + chunk) * P.T;
         if (DB && tid == 0 && chunk > c_begin) {  // gray / black totals of the PREVIOUS chunk are complete now
             u16* ccp = cc - P.T;
+            const u32 wrapped = any_prev ? 0u : (u32)CHUNK;
             ccp[P.T - (P.vp + 1)] = (u16)gb[set ^ 1][0];
-            ccp[P.T - 1] = (u16)gb[set ^ 1][1];
+            ccp[P.T - 1] = (u16)(gb[set ^ 1][1] + wrapped);
             gb[set ^ 1][0] = 0; gb[set ^ 1][1] = 0;
         }
+        // W3: (source pair of the chunk arrays, pair of the running sums it is added to, twin = its pixels have max 255)
+        auto drain3 = [&](int src, int dst, bool twin) -> u32 {
+            uint4* ap = reinterpret_cast<uint4*>(cw) + src;
+            const uint4 a = *ap;
+            if ((a.x | a.y | a.z | a.w) == 0) return 0;
+            saw = 1;
+            uint4* sp4 = reinterpret_cast<uint4*>(cw + ncs) + src;
+            uint4* hp4 = reinterpret_cast<uint4*>(cw + 2 * ncs) + src;
+            const uint4 sv = *sp4, hv = *hp4;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            *ap = z; *sp4 = z; *hp4 = z;
+            // count field; a cell that took the whole chunk wrapped it to 0 but kept its sum of max
+            auto cnt = [](u32 w0) -> u32 { const u32 c = w0 >> 20; return (c == 0 && w0 != 0) ? (u32)CHUNK : c; };
+            const uint4 n = make_uint4(cnt(a.x), cnt(a.y), cnt(a.z), cnt(a.w));
+            uint4* ac = reinterpret_cast<uint4*>(acc_cnt) + dst;
+            uint4* am = reinterpret_cast<uint4*>(acc_mx) + dst;
+            uint4 t = *ac; t.x += n.x; t.y += n.y; t.z += n.z; t.w += n.w; *ac = t;
+            if (twin) {
+                uint4* an = reinterpret_cast<uint4*>(acc_n255) + dst;
+                t = *an; t.x += n.x; t.y += n.y; t.z += n.z; t.w += n.w; *an = t;
+            }
+            t = *am; t.x += a.x & 0xfffffu; t.y += a.y & 0xfffffu; t.z += a.z & 0xfffffu; t.w += a.w & 0xfffffu; *am = t;
+            ulonglong2* as = reinterpret_cast<ulonglong2*>(acc_s) + 2 * dst;
+            ulonglong2* ah = reinterpret_cast<ulonglong2*>(acc_h) + 2 * dst;
+            ulonglong2 u = as[0]; u.x += sv.x - n.x * PHD_MAGIC_RN_BITS; u.y += sv.y - n.y * PHD_MAGIC_RN_BITS; as[0] = u;
+            u = as[1]; u.x += sv.z - n.z * PHD_MAGIC_RN_BITS; u.y += sv.w - n.w * PHD_MAGIC_RN_BITS; as[1] = u;
+            u = ah[0]; u.x += hv.x - n.x * PHD_MAGIC_RN_BITS; u.y += hv.y - n.y * PHD_MAGIC_RN_BITS; ah[0] = u;
+            u = ah[1]; u.x += hv.z - n.z * PHD_MAGIC_RN_BITS; u.y += hv.w - n.w * PHD_MAGIC_RN_BITS; ah[1] = u;
+            return n.x + n.y + n.z + n.w;
+        };
         // the four sub-cells of a (class, hue bin) pair are adjacent in every array: 16-byte accesses
         auto drain_pair = [&](int pair) -> u32 {
             uint4* w0p = reinterpret_cast<uint4*>(cw) + pair;
@@ -257,13 +324,28 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
         };
         for (int pair = tid; pair < npairs_colour; pair += THREADS) {
             const int cls = pair / hp, j = pair - cls * hp;
-            cc[j * spvp + cls] = (u16)drain_pair(pair);
+            if (W3) {
+                u32 n = drain3(pair, pair, false);
+                const int si = cls / P.vp;
+                if (cls - si * P.vp == P.vp - 1) n += drain3(twin_pair0 + si * hp + j, pair, true);  // top value bin: twin
+                cc[j * spvp + cls] = (u16)n;
+            } else {
+                cc[j * spvp + cls] = (u16)drain_pair(pair);
+            }
         }
         // gray and black: all hue bins collapse into one group each; handled by the LAST threads so that the
         // colour pairs and these spread over different warps
         for (int k = THREADS - 1 - tid; k < 2 * hp; k += THREADS) {
-            const int which = k / hp;
-            const u32 cnt = drain_pair((spvp + which) * hp + (k - which * hp));
+            const int which = k / hp, j = k - which * hp, pair = (spvp + which) * hp + j;
+            u32 cnt;
+            if (W3) {
+                cnt = drain3(pair, pair, false);
+                if (which == 0) cnt += drain3(twin_pair0 + P.sp * hp + j, pair, true);  // gray pixels with max 255
+                // the owner of the black pair of hue bin 0 repairs a wrapped all-black PREVIOUS chunk (see the barrier)
+                if (which == 1 && j == 0 && chunk > c_begin && !any_prev) acc_cnt[black_cell] += (u32)CHUNK;
+            } else {
+                cnt = drain_pair(pair);
+            }
             if (cnt) atomicAdd(&gb[set][which], cnt);
         }
         if (tid >= 64 && tid < 64 + P.vp - 1) cc[P.T - P.vp + (tid - 64)] = 0;  // gray groups 2.. are never used
@@ -276,12 +358,17 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
             }
         }
     }
-    __syncthreads();
+    const int any_last = W3 ? __syncthreads_or(saw) : (__syncthreads(), 1);
     if (DB && tid == 0 && c_end > c_begin) {
         const int set = (c_end - 1 - c_begin) & 1;
         u16* cc = counts_chunk + ((size_t)img * P.nchunks + (c_end - 1)) * P.T;
+        const u32 wrapped = any_last ? 0u : (u32)CHUNK;
         cc[P.T - (P.vp + 1)] = (u16)gb[set][0];
-        cc[P.T - 1] = (u16)gb[set][1];
+        cc[P.T - 1] = (u16)(gb[set][1] + wrapped);
+    }
+    if (W3 && c_end > c_begin && !any_last) {  // the last chunk was a wrapped all-black one
+        if (tid == 0) acc_cnt[black_cell] += (u32)CHUNK;
+        __syncthreads();
     }
 
     // flush the CTA's cell sums (Q20 in global memory whatever QS is) and the channel sums
@@ -528,6 +615,12 @@ __global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, unsigned
             cls = min(max(si, 0), P.sp - 1) * P.vp + vi;
         }
         svtab[((m * m + m) >> 1) + mn] = (unsigned char)cls;
+        // second table (three-word front end): pixels with max == 255 get the TWIN class of their class -- ncls + si
+        // for the top value bin of saturation bin si, ncls + sp for gray; black cannot occur there (bt <= 0.999999
+        // is a precondition of that kernel variant) and keeps its class
+        int cls3 = cls;
+        if (m == 255 && cls != spvp + 1) cls3 = P.ncls + (cls == spvp ? P.sp : cls / P.vp);
+        svtab[PHD_TRI_SIZE + ((m * m + m) >> 1) + mn] = (unsigned char)cls3;
     }
 }
 
@@ -581,11 +674,11 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-#define PHD_NCS_SMALL 640  // compile-time chunk-array stride of the 256-thread variant (cells + 32 scratch <= 640)
+#define PHD_NCS_SMALL 832  // compile-time chunk-array stride of the 256-thread variant (cells + twins + 32 scratch <= 832)
 
 size_t phd_pixels_smem(const DevParams& P) {
     const size_t ncs = (P.fe_threads == 256) ? PHD_NCS_SMALL : (size_t)P.NC + 32;
-    return phd_cell_tables_bytes() + (P.fe_threads == 256 ? 8 : 4) * ncs * sizeof(u32) + (size_t)P.NC * (2 * sizeof(u64) + 3 * sizeof(u32));
+    return phd_cell_tables_bytes() + (P.fe_threads == 256 ? 6 : 4) * ncs * sizeof(u32) + (size_t)P.NC * (2 * sizeof(u64) + 3 * sizeof(u32));
 }
 
 void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
@@ -645,4 +738,4 @@ void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev,
     if (exc_dev) k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
 }
 
-size_t phd_cell_tables_size() { return phd_cell_tables_bytes(); }
+size_t phd_cell_tables_size() { return 2 * phd_cell_tables_bytes(); }  // ordinary classes, then the table with twin classes

@@ -139,7 +139,7 @@ int check_params(phd_context* ctx, const phd_params* p, int max_boxes) {
         return fail(ctx, PHD_E_UNSUPPORTED, "s_partitions * v_partitions + 2 must fit one byte in this build");
     {
         const long long NC = ((long long)p->s_partitions * p->v_partitions + 2) * p->h_partitions * 4;
-        if (phd_cell_tables_size() + (size_t)(NC + 32) * 16 + (size_t)NC * 28 > 200 * 1024)
+        if (phd_cell_tables_size() / 2 + (size_t)(NC + 32) * 16 + (size_t)NC * 28 > 200 * 1024)  // one of the two tables
             return fail(ctx, PHD_E_UNSUPPORTED, "palette grid too fine for the shared-memory cells of this build");
     }
     if (!(p->black_thresh >= 0.0 && p->black_thresh < 1.0 && p->gray_thresh >= 0.0 && p->gray_thresh < 1.0))
@@ -166,8 +166,11 @@ void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_bo
     P.T = P.hp * P.sp * P.vp + P.vp + 1;
     P.ncls = P.sp * P.vp + 2;
     P.NC = P.ncls * P.hp * 4;
-    // three 256-thread CTAs per SM while the cells are small, one 512-thread CTA otherwise
-    P.fe_threads = (P.NC + 32 <= 640) ? 256 : 512;  // matches PHD_NCS_SMALL in frontend.cu
+    // three 256-thread CTAs per SM with the three-word chunk layout while the cells and their max == 255 twins fit
+    // its fixed stride (PHD_NCS_SMALL in frontend.cu) and the colour (0,0,0) is black but 255 is not; one 512-thread
+    // CTA with four words otherwise
+    const int twins = (P.sp + 1) * P.hp * 4;
+    P.fe_threads = (P.NC + twins + 32 <= 832 && p.black_thresh > 0.0 && p.black_thresh <= 0.999999) ? 256 : 512;
     P.chunk = P.fe_threads * 16;
     P.nchunks = (int)((P.hpx + P.chunk - 1) / P.chunk);
     // src/color_quantization.c:41-45

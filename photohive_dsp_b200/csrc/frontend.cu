@@ -113,10 +113,14 @@ __device__ __forceinline__ void run_step(CellRun& r, u32 base, u32 scratch, u32 
     const u32 addr = base + 4u * (u32)o.cell;
     const bool change = (addr != r.addr);
     run_emit<STRIDE_B, NW>(change ? r.addr : scratch, r, stride_b);
-    if (NW == 4) r.w0 = (change ? 0u : r.w0) + o.w0;
-    r.mx = (change ? 0u : r.mx) + (NW == 3 ? phd_w3_word0(o) : o.mx);
-    r.s = (change ? 0u : r.s) + o.sbits;
-    r.h = (change ? 0u : r.h) + o.hbits;
+    // accumulator = accumulator * keep + new: one multiply-add each instead of a select and an add (measured: neutral
+    // while the kernel was bound by four atomics per pixel, -2 % with three)
+    const u32 keep = change ? 0u : 1u;
+    const u32 m0 = NW == 3 ? phd_w3_word0(o) : o.mx;
+    if (NW == 4) asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r.w0) : "r"(keep), "r"(o.w0));
+    asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r.mx) : "r"(keep), "r"(m0));
+    asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r.s) : "r"(keep), "r"(o.sbits));
+    asm("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r.h) : "r"(keep), "r"(o.hbits));
     r.addr = addr;
 }
 

@@ -143,7 +143,7 @@ __device__ __forceinline__ void load48_aligned(const uint8_t* __restrict__ p, u3
 // NCS: compile-time stride (words) between the chunk word arrays, 0 = P.NC + 32 at run time.
 // DB: two chunk sets (one barrier per chunk); false = one set and a second barrier after the drain (large palettes).
 template <int THREADS, bool DS, int NCS, bool DB>
-__global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ rgb, DevParams P,
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1) k_pixels(const uint8_t* __restrict__ rgb, DevParams P,
                                                     const unsigned char* __restrict__ tabs_g,
                                                     const unsigned char* __restrict__ exc, int cpp,
                                                     u16* __restrict__ counts_chunk, u64* __restrict__ cells_g,
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     // the v clamp needs -- go to TWIN cells behind the ordinary ones (the twin class ids come straight out of a
     // second class table, so the pixel loop pays nothing) and are folded into their base cells by the drain.
     constexpr bool W3 = (THREADS == 256);
+    constexpr int W3_THREADS = W3 ? THREADS : 1;
     constexpr int NW = W3 ? 3 : 4;
     static_assert(!W3 || (NCS > 0 && DB), "the three-word layout is the double-buffered fixed-stride variant");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -171,6 +172,12 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     u32* acc_mx = acc_n255 + NC;
     __shared__ u64 red[6][THREADS / 32];
     __shared__ u32 gb[2][2];  // per chunk set: pixels of the gray and of the black group
+    // W3: the (class, hue bin) pair each thread drains after every chunk: x = pair | twin pair << 16 (0xffff: none),
+    // y = slot of the pair's group in the per-chunk group counts (0xffff: gray / black, summed through gb[]) |
+    // (0 gray, 1 black) << 16 | (repairs wrapped all-black chunks) << 17.  Pairs that have a twin (top value bin of every
+    // saturation bin, gray) sit together in the first warps and the others start at the next warp boundary, so that no
+    // warp runs the twin drain for a few lanes only.
+    __shared__ uint2 dmeta[W3_THREADS];
 
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
@@ -187,6 +194,25 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
     const int twin_pair0 = NC / 4;                  // first twin pair of the chunk arrays
     const int black_cell = (spvp + 1) * hp * 4 + 1; // cell of the colour (0,0,0)
     int saw = 0;                                    // this thread's last drain met a non-empty cell
+    if (W3) {
+        const int n_top = P.sp * hp, n_tw = n_top + hp, t0 = (n_tw + 31) & ~31;
+        const int per_s = (P.vp - 1) * hp, n_rest = P.sp * per_s, r = tid - t0;
+        u32 d_pair = 0xffff, d_twin = 0xffff, d_cc = 0xffff, flags = 0;
+        if (tid < n_top) {
+            const int si = tid / hp, j = tid - si * hp, cls = si * P.vp + P.vp - 1;
+            d_pair = cls * hp + j; d_twin = twin_pair0 + si * hp + j; d_cc = j * spvp + cls;
+        } else if (tid < n_tw) {
+            const int j = tid - n_top;
+            d_pair = spvp * hp + j; d_twin = twin_pair0 + P.sp * hp + j;
+        } else if (r >= 0 && r < n_rest) {
+            const int si = r / per_s, rem = r - si * per_s, vi = rem / hp, j = rem - vi * hp, cls = si * P.vp + vi;
+            d_pair = cls * hp + j; d_cc = j * spvp + cls;
+        } else if (r >= n_rest && r < n_rest + hp) {
+            const int j = r - n_rest;
+            d_pair = (spvp + 1) * hp + j; flags = 1u | (j == 0 ? 2u : 0u);
+        }
+        dmeta[tid] = make_uint2(d_pair | (d_twin << 16), d_cc | (flags << 16));
+    }
     {   // keep the table pointer in registers: the compiler would reload it from the constant bank per pixel
         unsigned long long e;
         asm volatile("mov.u64 %0, %1;" : "=l"(e) : "l"(exc));
@@ -326,31 +352,30 @@ __global__ void __launch_bounds__(THREADS) k_pixels(const uint8_t* __restrict__ 
             u = ah[1]; u.x += hv.z - n.z * PHD_MAGIC_RN_BITS; u.y += hv.w - n.w * PHD_MAGIC_RN_BITS; ah[1] = u;
             return n.x + n.y + n.z + n.w;
         };
-        for (int pair = tid; pair < npairs_colour; pair += THREADS) {
-            const int cls = pair / hp, j = pair - cls * hp;
-            if (W3) {
-                u32 n = drain3(pair, pair, false);
-                const int si = cls / P.vp;
-                if (cls - si * P.vp == P.vp - 1) n += drain3(twin_pair0 + si * hp + j, pair, true);  // top value bin: twin
-                cc[j * spvp + cls] = (u16)n;
-            } else {
+        if (W3) {
+            // this thread's pair (see dmeta): read here so that nothing about it stays live through the pixel loop
+            const uint2 dm = dmeta[tid];
+            const int d_pair = (int)(dm.x & 0xffffu), d_twin = (int)(dm.x >> 16), d_cc = (int)(dm.y & 0xffffu);
+            if (d_pair != 0xffff) {
+                u32 n = drain3(d_pair, d_pair, false);
+                if (d_twin != 0xffff) n += drain3(d_twin, d_pair, true);
+                if (d_cc != 0xffff) cc[d_cc] = (u16)n;
+                else if (n) atomicAdd(&gb[set][(dm.y >> 16) & 1u], n);
+                // the owner of the black pair of hue bin 0 repairs a wrapped all-black PREVIOUS chunk (see the barrier)
+                if ((dm.y >> 17) && chunk > c_begin && !any_prev) acc_cnt[black_cell] += (u32)CHUNK;
+            }
+        } else {
+            for (int pair = tid; pair < npairs_colour; pair += THREADS) {
+                const int cls = pair / hp, j = pair - cls * hp;
                 cc[j * spvp + cls] = (u16)drain_pair(pair);
             }
-        }
-        // gray and black: all hue bins collapse into one group each; handled by the LAST threads so that the
-        // colour pairs and these spread over different warps
-        for (int k = THREADS - 1 - tid; k < 2 * hp; k += THREADS) {
-            const int which = k / hp, j = k - which * hp, pair = (spvp + which) * hp + j;
-            u32 cnt;
-            if (W3) {
-                cnt = drain3(pair, pair, false);
-                if (which == 0) cnt += drain3(twin_pair0 + P.sp * hp + j, pair, true);  // gray pixels with max 255
-                // the owner of the black pair of hue bin 0 repairs a wrapped all-black PREVIOUS chunk (see the barrier)
-                if (which == 1 && j == 0 && chunk > c_begin && !any_prev) acc_cnt[black_cell] += (u32)CHUNK;
-            } else {
-                cnt = drain_pair(pair);
+            // gray and black: all hue bins collapse into one group each; handled by the LAST threads so that the
+            // colour pairs and these spread over different warps
+            for (int k = THREADS - 1 - tid; k < 2 * hp; k += THREADS) {
+                const int which = k / hp, j = k - which * hp;
+                const u32 cnt = drain_pair((spvp + which) * hp + j);
+                if (cnt) atomicAdd(&gb[set][which], cnt);
             }
-            if (cnt) atomicAdd(&gb[set][which], cnt);
         }
         if (tid >= 64 && tid < 64 + P.vp - 1) cc[P.T - P.vp + (tid - 64)] = 0;  // gray groups 2.. are never used
         if (!DB) {

@@ -170,7 +170,10 @@ void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_bo
     // its fixed stride (PHD_NCS_SMALL in frontend.cu) and the colour (0,0,0) is black but 255 is not; one 512-thread
     // CTA with four words otherwise
     const int twins = (P.sp + 1) * P.hp * 4;
-    P.fe_threads = (P.NC + twins + 32 <= 832 && p.black_thresh > 0.0 && p.black_thresh <= 0.999999) ? 256 : 512;
+    // (its drain gives every (class, hue bin) pair one thread: pairs with a twin first, the rest from the next warp on)
+    const int drain_threads = (((P.sp + 1) * P.hp + 31) & ~31) + (P.sp * (P.vp - 1) + 1) * P.hp;
+    P.fe_threads = (P.NC + twins + 32 <= 832 && drain_threads <= 256 && p.black_thresh > 0.0 && p.black_thresh <= 0.999999)
+                       ? 256 : 512;
     P.chunk = P.fe_threads * 16;
     P.nchunks = (int)((P.hpx + P.chunk - 1) / P.chunk);
     // src/color_quantization.c:41-45

@@ -101,7 +101,8 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
     if (num2 < 0.0f) num2 = fmaf(720.0f, qf, num2);    // h < 0 -> h + 360 (:398-404)
     const int cls = svtab[((mx * mx + mx) >> 1) + mn];
     // half-bin index and exact remainder
-    const float den = fmaxf(K.Lh * qf, 1.0f);          // q == 0: num2 == 0, any positive den gives half bin 0
+    // Lh*q exactly for q >= 1 (the tiny addend rounds away); q == 0: num2 == 0 and any positive den gives half bin 0
+    const float den = fmaf(K.Lh, qf, 1e-30f);
     const float rden = phd_rcp(den);
     const float y = fmaf(num2, rden, K.eps);
     const float hbm = __fadd_rd(y, PHD_MAGIC_FLOOR);   // bits: 0x4B000000 + floor(y)

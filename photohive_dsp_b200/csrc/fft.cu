@@ -642,12 +642,13 @@ __device__ __forceinline__ void cols_fix_dc(const DevParams& P, const ImageAcc* 
 // power -> (p < 1 ? 0 : ln p) as fixed point 2^-20 -> polar bin, run-length merged per thread (bins change slowly
 // along a column) into the shared integer bins.  Returns the running max of the RAW power (re^2 + im^2).
 // GT > 0: column c belongs to the thread group c (threads c*GT .. c*GT+GT-1, the group that transformed it).
-template <int SEG, int GT>
+// FULL: H is a multiple of SEG (no bounds check per element).
+template <int SEG, int GT, bool FULL = false>
 __device__ __forceinline__ float cols_accumulate(int H, int ncol, const float2* res, int cs, const u16* map, int ms,
                                                  u32* bin_lo, u32* bin_hi, float mymax) {
     const float thr = (float)PHD_POWER_SCALE;                            // p >= 1  <=>  raw >= 255000^2
-    const float lg2c = (float)(-2.0 * 17.960137721520944);               // log2(1 / 255000^2)
     const float kq = (float)(0.69314718055994530942 * (1 << PHD_LN_SHIFT));  // ln 2 * 2^20
+    const float lgq = (float)(-2.0 * 17.960137721520944 * 0.69314718055994530942 * (1 << PHD_LN_SHIFT));  // ln(1/255000^2) * 2^20
     const int segs = (H + SEG - 1) / SEG;
     const int first = GT > 0 ? (int)threadIdx.x % GT : (int)threadIdx.x;
     const int total = GT > 0 ? ((int)threadIdx.x / GT < ncol ? segs : 0) : ncol * segs;
@@ -659,13 +660,13 @@ __device__ __forceinline__ float cols_accumulate(int H, int ncol, const float2* 
         u32 run_sum = 0;
 #pragma unroll
         for (int i = 0; i < SEG; i++) {
-            if (k0 + i < H) {
+            if (FULL || k0 + i < H) {
                 const float2 v = rp[i];
                 const float raw = fmaf(v.x, v.x, v.y * v.y);
                 mymax = fmaxf(mymax, raw);
                 if (raw >= thr) {
-                    // clamped at 0: log2(raw) + lg2c can round a hair below 0 when p == 1
-                    const u32 q = (u32)__float2int_rn(fmaxf((__log2f(raw) + lg2c) * kq, 0.f));
+                    // ln p * 2^20 in one multiply-add; clamped at 0: it can round a hair below 0 when p == 1
+                    const u32 q = (u32)__float2int_rn(fmaxf(fmaf(__log2f(raw), kq, lgq), 0.f));
                     const int bin = mp[i];
                     if (bin != run_bin) {
                         if (run_sum) {
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_cols_t(DevParams P, const
         if (WRITE_POWER) cols_write_power(P, img, x0, ncol, res, N, power_out);
         else {
             constexpr int SEG = (NB * N + kColThreads - 1) / kColThreads;
-            mymax = cols_accumulate<SEG, GT>(P.H, ncol, res, N, smap + (it & 1) * NB * N, N, bin_lo, bin_hi, mymax);
+            mymax = cols_accumulate<SEG, GT, N % SEG == 0>(N, ncol, res, N, smap + (it & 1) * NB * N, N, bin_lo, bin_hi, mymax);
         }
         // bufB is rewritten by the next group's first pass: a column is binned and rewritten by the thread group
         // that transformed it, so the hand-over is that group's barrier (the test hook spreads its writes over

@@ -52,6 +52,22 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def check_record_zero(raw_record, lay):
+    """Outside the timed region: record 0 of the default workload (G0, seed 12345, 1920x1080, default parameters) must
+    equal the committed golden case `g0_1080p` -- outputs of the UNMODIFIED reference (tests/golden/make_golden.py) --
+    within the tolerances of tests/parity.py.  Raises AssertionError otherwise."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import Golden
+    from parity import assert_report_close, golden_report, report_from_batch
+    from photohive_dsp_b200.batch import view_records
+    g = Golden()
+    m = g.meta["g0_1080p"]
+    assert (m["kind"], m["seed"], m["W"], m["H"]) == (0, FIRST_SEED, W, H) and not m["params"] and not m["boxes"]
+    rec = np.ascontiguousarray(np.asarray(raw_record, np.uint8).reshape(1, -1))
+    assert_report_close(report_from_batch(view_records(rec, lay), 0), golden_report(g, "g0_1080p"), "bench record 0")
+    return "record 0 equals golden g0_1080p (unmodified reference) within tests/parity.py tolerances"
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation on the host cores
 # ------------------------------------------------------------------------------------------------

@@ -176,7 +176,7 @@ class Context:
         """images: uint8 [n,H,W,3] numpy array (host) or torch CUDA tensor (device, contiguous).
         boxes: None or int array [n, max_boxes, 4] of (top, bottom, left, right)."""
         params = params or make_params(**param_overrides)
-        ptr, n, H, W, stride, keep = _as_image_batch(images)
+        ptr, n, H, W, stride, keep = _as_image_batch(images, self.device)
         mb, bptr, bkeep = 0, None, None
         if boxes is not None:
             bkeep = np.ascontiguousarray(boxes, np.int32)
@@ -243,7 +243,7 @@ class Context:
         return out
 
 
-def _as_image_batch(images):
+def _as_image_batch(images, device=None):
     """-> (pointer, n, H, W, stride_bytes, keepalive)"""
     if isinstance(images, np.ndarray):
         a = images
@@ -264,5 +264,12 @@ def _as_image_batch(images):
             raise ValueError("images must be uint8 [n,H,W,3]")
         t = t.contiguous()
         n, H, W, _ = t.shape
+        if t.is_cuda:
+            # ordering contract of phd_get_reports_u8 (include/photohive_dsp.h): the library launches on its own
+            # non-blocking stream, so whatever produced the tensor (torch's current stream, the DMA tail of a
+            # pageable .cuda() copy) must have finished before the pointer is handed over
+            if device is not None and t.device.index != device:
+                raise ValueError(f"images live on cuda:{t.device.index} but the context belongs to cuda:{device}")
+            torch.cuda.current_stream(t.device).synchronize()
         return C.c_void_p(t.data_ptr()), n, H, W, H * W * 3, t
     raise TypeError(f"unsupported image container {type(images)!r}")

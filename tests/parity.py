@@ -12,6 +12,19 @@ implementation actually achieves is far tighter, and the tests pin that so regre
       2^-20 of a half hue bin, i.e. 1e-5 degree at h=18)       : 1e-5 absolute
   blur-profile bins (FP32 transform vs the reference's FP64)   : 1e-4 relative with a 2e-6 absolute floor
   blur-vector magnitudes (k / nr as float)                     : exact
+
+FFT magnitudes.  The transform runs in FP32 (SURVEY.md section 8d sanctions an FP32 complex intermediate); its error
+is ABSOLUTE in nature -- about 1e-7 of the spectrum's rms level per coefficient -- so a coefficient far below the rms
+level cannot be relative-accurate to 1e-4 in any FP32 transform.  tests/test_gpu_parity.py therefore asserts
+    |P - P_ref| <= 1e-4 * (P_ref + mean(P_ref))                  (P = |X|^2; the per-coefficient bound relative to the
+                                                                 coefficient PLUS the mean power level)
+and, separately, the north star's plain per-coefficient figure on the coefficients that carry the result:
+    |P - P_ref| / P_ref <= 1e-4 for every coefficient with P_ref >= 1e-3 * mean(P_ref)
+and it REPORTS (fft_error_report, printed with -s / -rP and kept in the test's user properties) the distribution of the
+plain per-coefficient relative error of the MAGNITUDE |X| (median / p99 / max over all coefficients) and the number of
+coefficients on the other side of the `p < 1 -> 0` threshold of pgm_normalize_fft (src/fft_processing.c:188-193) than in
+the float64 transform.  What reaches the report -- the blur-profile bins, means of ln p over hundreds of coefficients --
+is held to 1e-4 relative by assert_report_close.
 """
 import numpy as np
 
@@ -32,6 +45,24 @@ def rel_err(a, b, floor=1e-300):
         e = np.abs(a - b) / np.maximum(np.abs(b), floor)
     e = np.where(both, 0.0, e)
     return np.where(np.isnan(e), np.inf, e)
+
+
+def fft_error_report(pw, ref):
+    """pw: FP32 power spectrum of the product path, ref: float64 power spectrum (same shape).  Returns a dict with the
+    per-coefficient relative error of the magnitude |X| (median, p99, max, and max over the coefficients above 1e-3 of
+    the mean power) and the count of `p < 1` threshold flips."""
+    pw = np.asarray(pw, np.float64)
+    ref = np.asarray(ref, np.float64)
+    mag, mref = np.sqrt(pw), np.sqrt(ref)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(mag - mref) / mref
+    rel = np.where(mref == 0, np.where(mag == 0, 0.0, np.inf), rel)
+    big = ref >= 1e-3 * ref.mean()
+    flips = int(np.count_nonzero((pw < 1.0) != (ref < 1.0)))
+    return dict(n=int(ref.size), median=float(np.median(rel)), p99=float(np.quantile(rel, 0.99)), max=float(rel.max()),
+                max_significant=float(rel[big].max()) if big.any() else 0.0,
+                n_significant=int(big.sum()), threshold_flips=flips,
+                max_power_rel=float((np.abs(pw - ref) / (ref + ref.mean())).max()))
 
 
 def assert_report_close(got, want, what=""):

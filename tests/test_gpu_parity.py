@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle.binding import make_params as omake
-from parity import assert_report_close, boxes_array, golden_report, rel_err, report_from_batch
+from parity import assert_report_close, boxes_array, fft_error_report, golden_report, rel_err, report_from_batch
 from photohive_dsp_b200.batch import flat_layout, make_params
 
 pytestmark = pytest.mark.gpu
@@ -47,7 +47,7 @@ def test_group_counts_bit_exact(ctx, oracle, kind, kw):
 
 
 # ---- full reports ----------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["g1_small", "g0_small", "g2_small", "g1_odd2", "g0_fine", "g1_down5", "g1_list50", "g2_cov1",
+@pytest.mark.parametrize("name", ["g1_small", "g0_small", "g2_small", "g1_odd", "g1_odd2", "g0_fine", "g1_down5", "g1_list50", "g2_cov1",
                                   "g1_1080p", "g0_1080p", "g2_1080p"])
 def test_report_matches_reference_golden(ctx, oracle, golden, name):
     """Against outputs of the UNMODIFIED reference (tests/golden/make_golden.py)."""
@@ -83,6 +83,41 @@ def test_report_matches_oracle(ctx, oracle, W, H, kind, kw):
     assert np.array_equal(got.extra["parent_ids"], want.extra["parent_ids"])
     assert got.extra["tie_groups"] == want.extra["tie_groups"]
     assert got.extra["dropped_pixels"] == want.extra["dropped_pixels"]
+
+
+@pytest.mark.parametrize("W,H,kind,kw,nbox", [
+    (6000, 4000, 1, {}, 0),       # BASELINE config 4: 24 MP; saliencies pass 2^31 on their own
+    (6000, 4000, 0, {}, 2),       # 24 MP noise: 79 parents, 5,860 chunks per image, boxes on the large image
+    (1920, 1080, 0, FINE, 0),     # BASELINE config 5: h36 s4 v6 cov .99 at 1080p (the 512-thread front-end variant)
+    (1920, 1080, 1, FINE, 4),
+    (1920, 1080, 2, FINE, 0),
+    (4000, 6000, 1, dict(downsample_rate=2), 0),  # portrait 24 MP, downsampled HSV grid
+    (7680, 4320, 1, {}, 0),       # 33 MP: two groups' saliencies exceed 2^31 without any help from the weights
+])
+def test_full_report_at_baseline_sizes(ctx, oracle, W, H, kind, kw, nbox):
+    """BASELINE configs 4 and 5 as FULL reports against the oracle (the stages whose indexing changes with
+    the image size -- chunk counts, work lists, natural saliency overflow, the 6000/4000-point FFT epilogues -- and the
+    fine-palette front end at 1080p were only covered through invariants / small images)."""
+    img = oracle.generate(kind, 2024 + kind, W, H)
+    boxes = [dict(top=H * i // 8, bottom=H * i // 8 + H // 4, left=W * i // 8, right=W * i // 8 + W // 4)
+             for i in range(nbox)] or None
+    want = oracle.report(img, omake(**kw), boxes=boxes, nthreads=16)
+    b = ctx.get_reports(img[None], boxes=boxes_array(boxes), params=make_params(**kw))
+    got = report_from_batch(b, 0)
+    assert_report_close(got, want, f"{W}x{H} kind {kind} {kw}")
+    assert np.array_equal(got.extra["parent_ids"], want.extra["parent_ids"])
+    assert got.extra["tie_groups"] == want.extra["tie_groups"]
+    assert got.extra["dropped_pixels"] == want.extra["dropped_pixels"]
+    counts = ctx.debug_group_counts(img, make_params(**kw))
+    assert np.array_equal(counts, oracle.report(img, omake(**kw), stages=1).extra["group_counts"])
+    if (W, H) == (7680, 4320):
+        # the comparator's float -> int overflow (cvttss2si -> INT_MIN) is live here with the default weights
+        p = omake(**kw)
+        g = np.arange(p.h_partitions * p.s_partitions * p.v_partitions)
+        sc = ((g // p.v_partitions) % p.s_partitions + 0.5) * (1 - p.gray_thresh) / p.s_partitions + p.gray_thresh
+        vc = (g % p.v_partitions + 0.5) * (1 - p.black_thresh) / p.v_partitions + p.black_thresh
+        sal = counts[:len(g)] * (p.quantity_weight + p.saturation_value_weight * sc * vc) * 1000
+        assert (sal > 2.0 ** 31).sum() >= 1
 
 
 def _exceptional_colour_image(hp, W, H, seed, gray_fraction):
@@ -350,17 +385,24 @@ def test_non_8bit_image_is_refused_loudly(capfd):
                                  (3264, 2448), (2448, 3264), (4608, 3456), (3456, 4608), (1600, 1200), (1200, 1600),
                                  (1280, 960), (960, 1280), (2160, 3840), (1080, 1920), (4000, 6000), (480, 600), (600, 480),
                                  (2011, 1511), (1511, 2011), (4030, 3020), (1031, 523)])  # prime sides: the O(p^2) pass
-def test_power_spectrum_against_float64_fft(ctx, oracle, W, H):
-    """Every compile-time FFT plan (and two runtime-radix shapes) against numpy's float64 rfft2 of the same exact gray
-    numerators, element by element: |X|^2 of the hand-written FP32 transform within 1e-4 of (value + mean level)."""
+def test_power_spectrum_against_float64_fft(ctx, oracle, W, H, record_property):
+    """Every compile-time FFT plan (and the runtime-radix / Bluestein shapes) against numpy's float64 rfft2 of the same
+    exact gray numerators, element by element (bounds and what is reported: tests/parity.py, "FFT magnitudes")."""
     img = oracle.generate(0, 31 + W, W, H)
     pw = ctx.debug_power_spectrum(img).astype(np.float64)
     i64 = img.astype(np.int64)
     gnum = (299 * i64[:, :, 0] + 587 * i64[:, :, 1] + 114 * i64[:, :, 2]) - 127500
     ref = np.abs(np.fft.rfft2(gnum.astype(np.float64) / 255000.0)) ** 2
     assert pw.shape == ref.shape
+    rep = fft_error_report(pw, ref)
+    record_property("fft_error", rep)
+    print(f"FFT {W}x{H}: |X| rel err median {rep['median']:.2e} p99 {rep['p99']:.2e} max {rep['max']:.2e} "
+          f"(max over the {rep['n_significant']} coefficients >= 1e-3 of the mean power: {rep['max_significant']:.2e}); "
+          f"p<1 threshold flips: {rep['threshold_flips']} of {rep['n']}")
     err = np.abs(pw - ref) / (ref + ref.mean())
     assert err.max() < 1e-4, (W, H, float(err.max()), np.unravel_index(err.argmax(), err.shape))
+    assert 2 * rep["max_significant"] < 1e-4, rep   # power relative error = 2 x magnitude relative error
+    assert rep["median"] < 2e-6 and rep["p99"] < 1e-4, rep
 
 
 # ---- full-size, size-independent properties --------------------------------------------------------

@@ -216,6 +216,9 @@ PHD_API Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_
 PHD_API int phd_last_timing(const phd_context* ctx, float ms[8]);
 /* How many times each of those stages was launched in that call (sub-batches), same indexing; [0] = 1. */
 PHD_API int phd_last_stage_launches(const phd_context* ctx, int n[8]);
+/* 1 when that call ran the front end and the row FFT as ONE launch (role-switching persistent CTAs; its time is then
+ * reported as stage 1 and stage 4 is zero), 0 when they were two launches. */
+PHD_API int phd_last_fused(const phd_context* ctx);
 
 /* Test hooks (parity tests call these through the C ABI; they are not needed by applications). */
 PHD_API int phd_debug_group_sweep(phd_context* ctx, const phd_params* p, uint16_t* out_2pow24 /* host */);       /* product path (integer fast path + FP64 edge path) */

@@ -210,6 +210,10 @@ class Context:
         self._check(lib.phd_last_stage_launches(self._h, C.byref(n)))
         return dict(zip(self.STAGES, [int(x) for x in n]))
 
+    def last_fused(self) -> bool:
+        """True when the last call ran the front end and the row FFT as one launch (its time is under "frontend")."""
+        return bool(lib.phd_last_fused(self._h))
+
     # ---- test hooks ---------------------------------------------------------------------------------
     def debug_group_sweep(self, params: phd_params, exact: bool = False) -> np.ndarray:
         """Group id of all 2^24 colours: product path, or (exact=True) the FP64 transcription."""

@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include "fft_tables.cuh"
+#include "frontend_walk.cuh"
 #include "phd_internal.h"
 
 namespace {
@@ -435,18 +436,15 @@ constexpr int rows_min_blocks(int smem_bytes, int threads) {
     return by_smem < by_regs ? by_smem : by_regs;
 }
 
+// rows_walk: the body as a device function -- steps q_begin, q_begin + q_step, ... < q_end of image `img` -- shared by
+// k_rows_t (one walk per CTA) and the row role of k_front_rows (persistent CTAs, tasks from a queue).
 template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
-__global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 16) * 8, THREADS)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
-                                                    const float2* __restrict__ twp, float2* __restrict__ specT) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t* __restrict__ rgb, const DevParams& P,
+                                          const float2* __restrict__ twp, float2* __restrict__ specT, const int img,
+                                          const int q_begin, const int q_end, const int q_step) {
     constexpr int NP = N + N / 16;  // padded length
     float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [PAIRS][NP]  (also pass scratch: [PAIRS][N] fits)
     float2* bufB = bufA + PAIRS * NP;                    // [PAIRS][N]
-    const int img = blockIdx.y;
-    const int nsteps = P.H / (2 * PAIRS);
-    // steps blockIdx.x, blockIdx.x + gridDim.x, ...: CTAs that run together work on neighbouring rows, so the
-    // pieces they write into the same 128-byte lines of the transposed spectrum meet in L2
-    const int q_begin = blockIdx.x, q_end = nsteps, q_step = gridDim.x;
     const uint8_t* img_base = rgb + (size_t)img * P.image_stride;
     // Per step: PAIRS row pairs x N/16 segments of 16 pixels; one task (thread) holds the segment of BOTH rows of
     // its pair (2 x three 16-byte loads).  The loads of the next step are issued before the passes of this one and
@@ -502,6 +500,61 @@ __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 
         }
         // the next step's staging writes bufA (last read by pass 3, barrier passed); its first pass writes bufB
         // only after the barrier that follows the staging, i.e. after every thread finished this output loop
+    }
+}
+
+template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
+__global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 16) * 8, THREADS)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
+                                                    const float2* __restrict__ twp, float2* __restrict__ specT) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // steps blockIdx.x, blockIdx.x + gridDim.x, ...: CTAs that run together work on neighbouring rows, so the
+    // pieces they write into the same 128-byte lines of the transposed spectrum meet in L2
+    rows_walk<N, R0, R1, R2, R3, THREADS, PAIRS>(smem_raw, rgb, P, twp, specT, blockIdx.y, blockIdx.x, P.H / (2 * PAIRS),
+                                                 gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// Front end + row FFT as ONE launch of persistent, role-switching CTAs.  Both stages stream the same packed RGB; run
+// one after the other each leaves issue slots idle for a different reason (the front end stalls on its shared-memory
+// atomics and its per-chunk barrier, the row FFT on the latency between its short passes), and the second reader
+// finds nothing of the image in L2 any more.  Here every CTA (256 threads, the front end's shared memory, three per
+// SM) pops tasks from one queue that lists, image by image, the image's front-end walks and its row-FFT tasks
+// interleaved; at any moment the CTAs of an SM are a mix of both roles, working on the same few images, so the two
+// instruction streams fill each other's stalls and the second read of an image hits L2.  Tasks never wait for one
+// another (the column pass that needs both runs after this launch), so there is nothing to deadlock on.
+// A row task p of `row_parts` takes the steps p, p + row_parts, ...: tasks popped together write neighbouring rows.
+template <int N, int R0, int R1, int R2>
+__global__ void __launch_bounds__(256, 3) k_front_rows(const uint8_t* __restrict__ rgb, DevParams P,
+                                                       const unsigned char* __restrict__ tabs_g,
+                                                       const unsigned char* __restrict__ exc,
+                                                       u16* __restrict__ counts_chunk, u64* __restrict__ cells_g,
+                                                       u32* __restrict__ span32, u64* __restrict__ span64,
+                                                       ImageAcc* __restrict__ iacc, const float2* __restrict__ twp,
+                                                       float2* __restrict__ specT, u32* __restrict__ queue, int nimg,
+                                                       int row_parts) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ u32 s_task;
+    const u32 tpi = (u32)(P.nspans + row_parts);  // tasks per image
+    const u32 total = (u32)nimg * tpi;
+    bool table_in_smem = false;
+    for (;;) {
+        __syncthreads();  // the previous task is done with the shared memory (and s_task has been read)
+        if (threadIdx.x == 0) s_task = atomicAdd(queue, 1u);
+        __syncthreads();
+        const u32 t = s_task;
+        if (t >= total) break;
+        const int img = (int)(t / tpi), k = (int)(t - (u32)img * tpi);
+        // tasks 0 .. tpi-1 of an image: row tasks spread evenly among the walks (r = row tasks before task k)
+        const int r = (int)(((long long)k * row_parts) / tpi), r1 = (int)(((long long)(k + 1) * row_parts) / tpi);
+        if (r1 > r) {
+            rows_walk<N, R0, R1, R2, 1, 256, 2>(smem_raw, rgb, P, twp, specT, img, r, P.H / 4, row_parts);
+            table_in_smem = false;
+        } else {
+            const int span = k - r, c_begin = span * P.cpp, c_end = min(c_begin + P.cpp, P.nchunks);
+            fe_walk<256, false, PHD_NCS_SMALL, true>(smem_raw, rgb, P, tabs_g, exc, img, span, c_begin, c_end,
+                                                     !table_in_smem, counts_chunk, cells_g, span32, span64, iacc);
+            table_in_smem = true;
+        }
     }
 }
 
@@ -1035,9 +1088,45 @@ static void launch_rows_staged_if(const uint8_t* rgb, const DevParams& P, int ni
     }
 }
 
+// Lengths the fused front-end + row kernel is built for: the row role must fit the front end's CTA (256 threads, i.e.
+// at most 128 sixteen-pixel segments per row, two row pairs) and its shared memory (three CTAs per SM).
+template <int N, int R0>
+constexpr bool fused_ok() { return rows_t_ok<N, R0>() && N / 16 <= 128 && 2 * (2 * N + N / 16) * 8 <= 70 * 1024; }
+template <int N, int R0, int R1, int R2>
+static void launch_front_rows_if(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                                 const unsigned char* exc, const float2* twp, Workspace& ws, cudaStream_t st) {
+    if constexpr (fused_ok<N, R0>()) {
+        size_t smem = (size_t)2 * (2 * N + N / 16) * sizeof(float2);
+        if (phd_pixels_smem(P) > smem) smem = phd_pixels_smem(P);
+        PHD_ALLOW_SMEM((k_front_rows<N, R0, R1, R2>), 100 * 1024);
+        // row tasks about as long as a front-end walk (measured alone: a walk of 32 chunks ~ 1/16 of 6.2 us x 444 CTAs,
+        // the rows of an image ~ 4.3 us x 444 CTAs): H/4 steps split into parts of ~24 steps
+        int parts = (P.H / 4 + 23) / 24;
+        if (parts < 1) parts = 1;
+        const long long tasks = (long long)nimg * (P.nspans + parts);
+        const int grid = (int)(tasks < 148 * 3 ? tasks : 148 * 3);
+        k_front_rows<N, R0, R1, R2><<<grid, 256, smem, st>>>(rgb, P, tabs, exc, ws.counts_chunk, ws.cells, ws.span32,
+                                                             ws.span64, ws.iacc, twp, ws.spec, ws.queue, nimg, parts);
+    }
+}
+
 static bool rows_fast_ok(const DevParams& P) {
     int r[4];
     return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && special_radices(P.W, r);
+}
+
+// Front end and row FFT of `nimg` images as one launch (see k_front_rows); returns false when this shape / parameter
+// set has no fused kernel (the caller then launches the two stages separately).
+bool phd_launch_front_rows(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                           const unsigned char* exc, const FftPlan& row, Workspace& ws, cudaStream_t st, int* launches) {
+    if (P.fe_threads != 256 || P.ds > 1 || !rows_fast_ok(P)) return false;
+    switch (P.W) {
+#define PHD_X(N, R0, R1, R2, NB) \
+    case N: if (fused_ok<N, R0>()) { launch_front_rows_if<N, R0, R1, R2>(rgb, P, nimg, tabs, exc, row.twp, ws, st); *launches += 1; return true; } break;
+        PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
+    }
+    return false;
 }
 
 int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* specT,

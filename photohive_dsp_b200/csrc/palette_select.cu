@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                                                         int* __restrict__ tie_n, int* __restrict__ tie_groups,
                                                         long long* __restrict__ dropped, SlotAcc* __restrict__ sacc,
                                                         u32* __restrict__ hist, ImageAcc* __restrict__ iacc,
-                                                        u64* __restrict__ cells_tie_g, u32* __restrict__ work,
+                                                        u64* __restrict__ cells_tie_g,
+                                                        const u32* __restrict__ span32,
+                                                        const u64* __restrict__ span64, u32* __restrict__ work,
                                                         u32* __restrict__ work_n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = P.T, tid = threadIdx.x, img = blockIdx.x;
@@ -291,6 +293,8 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
             const int tk = take[g];
             int cum = 0, cstar = -1, need = 0, clast = -1;
             bool found = (tk == 0);
+            // pass 1: the chunk c* where the accepted prefix of `tk` pixels ends, how many pixels of c* are still
+            // accepted, and the chunk of the group's last pixel
             for (int base = 0; base < P.nchunks; base += 32) {
                 const int c = base + lane;
                 const int k = c < P.nchunks ? (int)cc[(size_t)c * T] : 0;
@@ -304,7 +308,6 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                 if (nz) clast = base + 31 - __clz(nz);
                 if (!found) {
                     const int before = cum + incl - k;
-                    if (k > 0 && before < tk) atomicOr(&cbits[c >> 5], 1u << (c & 31));
                     const unsigned hit = __ballot_sync(0xffffffffu, k > 0 && cum + incl >= tk);
                     if (hit) {
                         const int L = __ffs(hit) - 1;
@@ -316,6 +319,14 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                 }
             }
             if (!keep[g]) clast = -1;
+            // Every front-end walk (span of P.cpp chunks) that ends before c* is accepted as a whole: its cells come
+            // from the walk's stored sums.  Only the chunks of c*'s own span up to c* (and the chunk of the last
+            // pixel) are looked at again by the tie kernel.
+            const int sstar = cstar >= 0 ? cstar / P.cpp : 0;
+            const int c_first = sstar * P.cpp;
+            if (cstar >= 0)
+                for (int c = c_first + lane; c <= cstar; c += 32)
+                    if (cc[(size_t)c * T] > 0 && (c < cstar || need > 0)) atomicOr(&cbits[c >> 5], 1u << (c & 31));
             if (lane == 0) {
                 GroupPlan* gp = plan_g + (size_t)img * T + g;
                 gp->cstar = cstar;
@@ -323,11 +334,19 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                 gp->clast = clast;
                 if (clast >= 0) atomicOr(&cbits[clast >> 5], 1u << (clast & 31));
             }
-            // its tie cells start from zero
+            // its tie cells: the sums of the wholly accepted spans (zero when there is none)
             u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
             int c0, nc;
             phd_group_cell_range(P, g, &c0, &nc);
-            for (int i = lane; i < PHD_CELL_Q * nc; i += 32) ct[(size_t)(i / nc) * P.NC + c0 + (i % nc)] = 0;
+            for (int i = lane; i < PHD_CELL_Q * nc; i += 32) {
+                const int q = i / nc, cell = c0 + (i % nc);
+                u64 v = 0;
+                for (int sp = 0; sp < sstar; sp++) {
+                    const size_t sidx = (size_t)img * P.nspans + sp;
+                    v += q < 3 ? (u64)span32[(sidx * 3 + q) * P.NC + cell] : span64[(sidx * 2 + (q - 3)) * P.NC + cell];
+                }
+                ct[(size_t)q * P.NC + cell] = v;
+            }
         }
     }
     __syncthreads();
@@ -349,6 +368,6 @@ void phd_launch_palette_select(const DevParams& P, int nimg, const double* centr
     PHD_ALLOW_SMEM((k_palette_select), 200 * 1024);
     k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.cells, ws.counts_chunk, ws.plan, ws.pal_n,
                                               ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped, ws.sacc,
-                                              ws.hist, ws.iacc, ws.cells_tie, ws.work, ws.work_n);
+                                              ws.hist, ws.iacc, ws.cells_tie, ws.span32, ws.span64, ws.work, ws.work_n);
     *launches += 1;
 }

@@ -12,6 +12,7 @@
 #define PHD_MAX_GROUPS 2048   // T = h*s*v + v + 1 upper bound (shared-memory tables)
 #define PHD_MAX_BINS 8192     // na*nr upper bound
 #define PHD_MAX_FACTORS 24
+#define PHD_NCS_SMALL 832     // compile-time chunk-array stride of the 256-thread front end (cells + twins + 32 scratch <= 832)
 
 // Fixed-point scales of the integer accumulators (all sums are exact integers => order independent).
 #define PHD_S_SHIFT 20        // saturation and hue fraction of the palette cells: value * 2^20
@@ -44,6 +45,7 @@ struct DevParams {
     int fe_threads;      // front-end CTA size (256 or 512); a chunk is fe_threads * 16 HSV pixels
     int chunk;
     int nchunks;         // ceil(hpx / chunk)
+    int cpp, nspans;     // front-end walk: chunks per walk (span) and spans per image, set per launch (phd_fe_plan)
     int hp, sp, vp, T;
     int ncls, NC;        // palette classes sp*vp+2 and cells ncls*hp*4 (pixel_cells.cuh)
     double Lh, Ls, Lv, bt, gt;
@@ -102,8 +104,11 @@ struct Workspace {
     u16* counts_chunk;   // [cap][nchunks][T]
     u64* cells;          // [cap][PHD_CELL_Q][NC]   zeroed per sub-batch, filled by the front end
     u64* cells_tie;      // [cap][PHD_CELL_Q][NC]   cells of the partly accepted tie groups (zeroed by palette_select)
+    u32* span32;         // [spans of the launch][3][NC]  per front-end walk: count, n255, sum max
+    u64* span64;         // [spans of the launch][2][NC]  per front-end walk: sum s, sum hue fraction (both * 2^20)
     u32* work;           // [cap * nchunks]         (image, chunk) items of the tie path
     u32* work_n;         // [1]
+    u32* queue;          // [1] task counter of the fused front-end + row kernel
     u32* hist;           // [cap][T]
     ImageAcc* iacc;      // [cap]
     GroupPlan* plan;     // [cap][T]
@@ -120,6 +125,27 @@ struct Workspace {
     SharpAcc* sharp;     // [cap][max_boxes]
     int* boxes;          // [cap][max_boxes][4]
 };
+
+// Front-end walk plan: a CTA (or a front-end task of the fused kernel) walks `cpp` consecutive chunks of one image --
+// long walks amortise the table load and the final flush, but there must be enough walks to fill 148 SMs.
+static inline void phd_fe_plan(DevParams& P, int nimg) {
+    const long long total = (long long)P.nchunks * nimg;
+    int cpp = (int)(total / (148 * 12));
+    cpp = cpp < 1 ? 1 : (cpp > 32 ? 32 : cpp);
+    P.cpp = cpp;
+    P.nspans = (P.nchunks + cpp - 1) / cpp;
+}
+// Largest number of walks any launch of up to `cap` images can have (sizes span32 / span64).
+static inline size_t phd_fe_max_spans(const DevParams& P0, int cap) {
+    DevParams P = P0;
+    size_t m = 0;
+    for (int n = 1; n <= cap; n++) {
+        phd_fe_plan(P, n);
+        const size_t t = (size_t)P.nspans * n;
+        if (t > m) m = t;
+    }
+    return m;
+}
 
 // ---- launchers (each in its own .cu) --------------------------------------------------------
 void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
@@ -139,6 +165,8 @@ int phd_fft_plan_factors(int n, int* fac, int* nfac);  // 0 ok, nonzero unsuppor
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st);
 size_t phd_fft_pass_table_entries(const FftPlan& pl);
 void phd_fft_fill_pass_tables(float2* dev, FftPlan& pl, cudaStream_t st);  // also sets pl.twp_off / pl.twp
+bool phd_launch_front_rows(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
+                           const unsigned char* exc, const FftPlan& row, Workspace& ws, cudaStream_t st, int* launches);
 int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* spec,
                         cudaStream_t st, int* launches);
 int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* spec, const u16* binmap,

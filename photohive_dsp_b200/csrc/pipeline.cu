@@ -79,6 +79,7 @@ struct phd_context {
     float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int last_stage_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int last_launches = 0;
+    int last_fused = 0;  // the last call ran front end + row FFT as one launch (its time is reported as stage 1)
     char err[512] = {0};
 };
 
@@ -302,7 +303,7 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft)
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
-    cudaFree(w.cells_tie); cudaFree(w.work);
+    cudaFree(w.cells_tie); cudaFree(w.work); cudaFree(w.span32); cudaFree(w.span64);
     cudaFree(ctx->ws_zero);
     memset(&w, 0, sizeof(w));
     ctx->ws_zero = nullptr;
@@ -311,6 +312,11 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft)
     CUDA_TRY(ctx, cudaMalloc(&w.plan, sizeof(GroupPlan) * c * T));
     CUDA_TRY(ctx, cudaMalloc(&w.cells_tie, sizeof(u64) * c * PHD_CELL_Q * P.NC));
     CUDA_TRY(ctx, cudaMalloc(&w.work, sizeof(u32) * c * P.nchunks));
+    {
+        const size_t spans = phd_fe_max_spans(P, cap);
+        CUDA_TRY(ctx, cudaMalloc(&w.span32, sizeof(u32) * spans * 3 * P.NC));
+        CUDA_TRY(ctx, cudaMalloc(&w.span64, sizeof(u64) * spans * 2 * P.NC));
+    }
     CUDA_TRY(ctx, cudaMalloc(&w.pal_n, sizeof(int) * c));
     CUDA_TRY(ctx, cudaMalloc(&w.parent_ids, sizeof(int) * c * T));
     CUDA_TRY(ctx, cudaMalloc(&w.tie_list, sizeof(int) * c * T));
@@ -329,6 +335,7 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft)
     const size_t o_sharp = off; off = align_up(off + sizeof(SharpAcc) * c * (P.max_boxes > 0 ? P.max_boxes : 1), 256);
     const size_t o_cells = off; off = align_up(off + sizeof(u64) * c * PHD_CELL_Q * P.NC, 256);
     const size_t o_workn = off; off = align_up(off + sizeof(u32), 256);
+    const size_t o_queue = off; off = align_up(off + sizeof(u32), 256);
     CUDA_TRY(ctx, cudaMalloc(&ctx->ws_zero, off));
     ctx->ws_zero_bytes = off;
     w.hist = reinterpret_cast<u32*>(ctx->ws_zero + o_hist);
@@ -339,6 +346,7 @@ int ensure_workspace(phd_context* ctx, const DevParams& P, int cap, int cap_fft)
     w.sharp = reinterpret_cast<SharpAcc*>(ctx->ws_zero + o_sharp);
     w.cells = reinterpret_cast<u64*>(ctx->ws_zero + o_cells);
     w.work_n = reinterpret_cast<u32*>(ctx->ws_zero + o_workn);
+    w.queue = reinterpret_cast<u32*>(ctx->ws_zero + o_queue);
     w.capacity = cap;
     memcpy(ctx->ws_key, key, sizeof(key));
     return PHD_OK;
@@ -566,8 +574,15 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
         // records carry padding bytes no kernel writes: clear them so equal images give equal bytes
         CUDA_TRY(ctx, cudaMemsetAsync(records_dev + (size_t)first * lay.record_bytes, 0, lay.record_bytes * (size_t)n, st));
+        phd_fe_plan(P, n);
         mark(&e0);
-        phd_launch_pixels(d_in, P, n, tab->tabs, tab->exc, ctx->ws, st, &launches);
+        // front end and row FFT as one launch of role-switching CTAs where a fused kernel exists for the shape (fft.cu:
+        // k_front_rows) and the spectra of the whole group fit the spectrum buffer; two launches otherwise
+        static const bool fuse_enabled = !(getenv("PHD_FUSED") && atoi(getenv("PHD_FUSED")) == 0);
+        const bool fused = fuse_enabled && fb >= n &&
+                           phd_launch_front_rows(d_in, P, n, tab->tabs, tab->exc, shape->row, ctx->ws, st, &launches);
+        ctx->last_fused = fused ? 1 : 0;
+        if (!fused) phd_launch_pixels(d_in, P, n, tab->tabs, tab->exc, ctx->ws, st, &launches);
         mark(&e1); span(ST_FRONT, e0, e1); e0 = e1;
         phd_launch_palette_select(P, n, tab->centres, tab->sv_f, ctx->ws, st, &launches);
         mark(&e1); span(ST_SELECT, e0, e1); e0 = e1;
@@ -579,9 +594,11 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
             sub.iacc += f0;
             sub.binsum += (size_t)f0 * P.nbins;
             sub.maxpow += f0;
-            if (phd_launch_fft_rows(d_in + (size_t)f0 * dev_stride, P, nf, shape->row, ctx->ws.spec, st, &launches))
-                return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
-            mark(&e1); span(ST_ROWS, e0, e1); e0 = e1;
+            if (!fused) {
+                if (phd_launch_fft_rows(d_in + (size_t)f0 * dev_stride, P, nf, shape->row, ctx->ws.spec, st, &launches))
+                    return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
+                mark(&e1); span(ST_ROWS, e0, e1); e0 = e1;
+            }
             if (phd_launch_fft_cols_blur(P, nf, shape->col, ctx->ws.spec, shape->binmap, sub, nullptr, st, &launches))
                 return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
             mark(&e1); span(ST_COLS, e0, e1); e0 = e1;
@@ -703,7 +720,7 @@ void phd_context_destroy(phd_context* ctx) {
     Workspace& w = ctx->ws;
     cudaFree(w.counts_chunk); cudaFree(w.plan); cudaFree(w.pal_n); cudaFree(w.parent_ids); cudaFree(w.tie_list);
     cudaFree(w.tie_n); cudaFree(w.tie_groups); cudaFree(w.dropped); cudaFree(w.spec); cudaFree(w.boxes);
-    cudaFree(w.cells_tie); cudaFree(w.work);
+    cudaFree(w.cells_tie); cudaFree(w.work); cudaFree(w.span32); cudaFree(w.span64);
     cudaFree(ctx->ws_zero); cudaFree(ctx->d_rgb); cudaFree(ctx->d_records);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_u8); cudaFree(ctx->d_flag);
@@ -784,6 +801,8 @@ int phd_last_timing(const phd_context* ctx, float ms[8]) {
     for (int i = 0; i < 8; i++) ms[i] = ctx->last_ms[i];
     return ctx->last_launches;
 }
+
+int phd_last_fused(const phd_context* ctx) { return ctx ? ctx->last_fused : 0; }
 
 int phd_last_stage_launches(const phd_context* ctx, int n[8]) {
     if (!ctx) return PHD_E_BAD_PARAMS;
@@ -940,6 +959,7 @@ int phd_debug_group_counts(phd_context* ctx, const uint8_t* rgb, int width, int 
     int launches = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_rgb, rgb, tight, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, ctx->stream));
+    phd_fe_plan(P, 1);
     phd_launch_pixels(ctx->d_rgb, P, 1, tab->tabs, tab->exc, ctx->ws, ctx->stream, &launches);
     phd_launch_palette_select(P, 1, tab->centres, tab->sv_f, ctx->ws, ctx->stream, &launches);
     CUDA_TRY(ctx, cudaMemcpyAsync(counts, ctx->ws.hist, sizeof(int) * P.T, cudaMemcpyDeviceToHost, ctx->stream));

@@ -56,6 +56,8 @@ lib.phd_last_timing.restype = C.c_int
 lib.phd_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float * 8)]
 lib.phd_last_stage_launches.restype = C.c_int
 lib.phd_last_stage_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int * 8)]
+lib.phd_last_fused.restype = C.c_int
+lib.phd_last_fused.argtypes = [C.c_void_p]
 lib.phd_debug_group_sweep.restype = C.c_int
 lib.phd_debug_group_sweep.argtypes = [C.c_void_p, C.POINTER(phd_params), C.c_void_p]
 lib.phd_debug_group_sweep_exact.restype = C.c_int
@@ -69,6 +71,7 @@ lib.phd_debug_group_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
 
 EXPORTED = ["get_full_report_data", "free_full_report", "get_blur_profile_visual", "phd_default_params",
             "phd_context_create", "phd_context_destroy", "phd_last_error", "phd_flat_get_layout",
-            "phd_get_reports_u8", "phd_flat_to_full_report", "phd_last_timing", "phd_last_stage_launches", "phd_debug_group_sweep",
+            "phd_get_reports_u8", "phd_flat_to_full_report", "phd_last_timing", "phd_last_stage_launches", "phd_last_fused",
+            "phd_debug_group_sweep",
             "phd_debug_group_sweep_exact",
             "phd_debug_bin_map", "phd_debug_power_spectrum", "phd_debug_group_counts"]

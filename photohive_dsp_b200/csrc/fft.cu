@@ -26,6 +26,7 @@
 // 2..13, 15..19, 21, 25 and an O(p^2) pass for any other prime p: slow for large p -- a prime side of 2011 pixels costs
 // about a millisecond per image -- but arbitrary crops are served rather than refused).
 #include <math.h>
+#include <stdlib.h>
 
 #include "fft_tables.cuh"
 #include "frontend_walk.cuh"
@@ -438,7 +439,7 @@ constexpr int rows_min_blocks(int smem_bytes, int threads) {
 
 // rows_walk: the body as a device function -- steps q_begin, q_begin + q_step, ... < q_end of image `img` -- shared by
 // k_rows_t (one walk per CTA) and the row role of k_front_rows (persistent CTAs, tasks from a queue).
-template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
+template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS, bool PREFETCH = true>
 __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t* __restrict__ rgb, const DevParams& P,
                                           const float2* __restrict__ twp, float2* __restrict__ specT, const int img,
                                           const int q_begin, const int q_end, const int q_step) {
@@ -463,16 +464,17 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
         a0 = __ldg(s0); b0 = __ldg(s0 + 1); c0 = __ldg(s0 + 2);
         a1 = __ldg(s1); b1 = __ldg(s1 + 1); c1 = __ldg(s1 + 2);
     };
-    if (has_task && q_begin < q_end) load_step(q_begin);
+    if (PREFETCH && has_task && q_begin < q_end) load_step(q_begin);
     const int fw = N / 2 + 1;
     for (int q = q_begin; q < q_end; q += q_step) {
         if (has_task) {
+            if (!PREFETCH) load_step(q);  // no registers held across the passes (fused kernel)
             const u32 w0[12] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, c0.z, c0.w};
             const u32 w1[12] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, c1.z, c1.w};
             float2* dst = bufA + pair * NP + seg * 17;
 #pragma unroll
             for (int i = 0; i < 16; i++) dst[i] = make_float2((float)gray16(w0, i), (float)gray16(w1, i));
-            if (q + q_step < q_end) load_step(q + q_step);
+            if (PREFETCH && q + q_step < q_end) load_step(q + q_step);
         }
         __syncthreads();  // CTA wide: the previous step's output loop (all threads read every pair's result) is over
         const float2* z = fft_run_t<N, R0, R1, R2, R3, true, GT, false>(bufA, bufB, twp, PAIRS, NP, N);
@@ -523,6 +525,9 @@ __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 
 // instruction streams fill each other's stalls and the second read of an image hits L2.  Tasks never wait for one
 // another (the column pass that needs both runs after this launch), so there is nothing to deadlock on.
 // A row task p of `row_parts` takes the steps p, p + row_parts, ...: tasks popped together write neighbouring rows.
+// Neither role prefetches into registers here (PREFETCH = false): with the 80 registers three CTAs per SM allow, the
+// front end's 12 and the row stage's 24 prefetch registers were spilled (31 M local loads per 256 images, served by L2
+// because the shared-memory carve-out leaves almost no L1); the other roles' CTAs cover the exposed load latency.
 template <int N, int R0, int R1, int R2>
 __global__ void __launch_bounds__(256, 3) k_front_rows(const uint8_t* __restrict__ rgb, DevParams P,
                                                        const unsigned char* __restrict__ tabs_g,
@@ -547,17 +552,18 @@ __global__ void __launch_bounds__(256, 3) k_front_rows(const uint8_t* __restrict
         // tasks 0 .. tpi-1 of an image: row tasks spread evenly among the walks (r = row tasks before task k)
         const int r = (int)(((long long)k * row_parts) / tpi), r1 = (int)(((long long)(k + 1) * row_parts) / tpi);
         if (r1 > r) {
-            rows_walk<N, R0, R1, R2, 1, 256, 2>(smem_raw, rgb, P, twp, specT, img, r, P.H / 4, row_parts);
+            rows_walk<N, R0, R1, R2, 1, 256, 2, false>(smem_raw, rgb, P, twp, specT, img, r, P.H / 4, row_parts);
             table_in_smem = false;
         } else {
             const int span = k - r, c_begin = span * P.cpp, c_end = min(c_begin + P.cpp, P.nchunks);
-            fe_walk<256, false, PHD_NCS_SMALL, true>(smem_raw, rgb, P, tabs_g, exc, img, span, c_begin, c_end,
-                                                     !table_in_smem, counts_chunk, cells_g, span32, span64, iacc);
+            fe_walk<256, false, PHD_NCS_SMALL, true, true>(smem_raw, rgb, P, tabs_g, exc, img, span, c_begin, c_end,
+                                                            !table_in_smem, counts_chunk, cells_g, span32, span64, iacc);
             table_in_smem = true;
         }
     }
 }
 
+// ------------------------------------------------------------------------------------------
 // Rows, generic (any width, runtime radix plan): a CTA walks strided groups of 2*NP rows (NP = 2: quads).  The rows'
 // bytes are staged into shared memory (16-byte vector loads when the rows are 16-byte aligned), each thread then
 // converts "its" pixels of the NP row pairs to gray numerators, NP packed complex sequences are transformed, and every
@@ -1102,6 +1108,7 @@ static void launch_front_rows_if(const uint8_t* rgb, const DevParams& P, int nim
         // row tasks about as long as a front-end walk (measured alone: a walk of 32 chunks ~ 1/16 of 6.2 us x 444 CTAs,
         // the rows of an image ~ 4.3 us x 444 CTAs): H/4 steps split into parts of ~24 steps
         int parts = (P.H / 4 + 23) / 24;
+        if (getenv("PHD_ROW_PARTS")) parts = atoi(getenv("PHD_ROW_PARTS"));
         if (parts < 1) parts = 1;
         const long long tasks = (long long)nimg * (P.nspans + parts);
         const int grid = (int)(tasks < 148 * 3 ? tasks : 148 * 3);

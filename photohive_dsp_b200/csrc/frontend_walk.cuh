@@ -136,7 +136,7 @@ __device__ __forceinline__ void load48_aligned(const uint8_t* __restrict__ p, u3
 // that lies wholly before a tie group's cut-off chunk without looking at a pixel again (palette_select.cu).
 // load_table: the class table is not in shared memory yet (first walk of a CTA, or another role used the memory).
 // The caller guarantees a CTA-wide barrier between the previous user of the shared memory and this call.
-template <int THREADS, bool DS, int NCS, bool DB>
+template <int THREADS, bool DS, int NCS, bool DB, bool PREFETCH = true>
 __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* __restrict__ rgb, const DevParams& P,
                                         const unsigned char* __restrict__ tabs_g,
                                         const unsigned char* __restrict__ exc, const int img, const int span,
@@ -222,7 +222,7 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
     u32 w[12];
     {
         const long long p0 = (long long)c_begin * CHUNK + (long long)tid * 16;
-        if (fast_ok && p0 + 16 <= P.hpx) load48_aligned(base + p0 * 3, w);
+        if (PREFETCH && fast_ok && p0 + 16 <= P.hpx) load48_aligned(base + p0 * 3, w);
     }
     for (int chunk = c_begin; chunk < c_end; chunk++) {
         const int set = DB ? ((chunk - c_begin) & 1) : 0;
@@ -230,10 +230,14 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
         const u32 scratch = cw_base + 4u * (u32)(NCW + lane);
         const long long p0 = (long long)chunk * CHUNK + (long long)tid * 16;
         if (fast_ok && p0 + 16 <= P.hpx) {
+            // PREFETCH: the next chunk's bytes are in flight (12 registers) while this one is processed; without it the
+            // chunk's own bytes are loaded here (the fused kernel, where other roles' CTAs cover the latency and the
+            // registers are needed)
             u32 wn[12];
             const long long pn = p0 + CHUNK;
-            const bool more = (chunk + 1 < c_end) && (pn + 16 <= P.hpx);
-            if (more) load48_aligned(base + pn * 3, wn);  // next chunk's bytes are in flight while this one is processed
+            const bool more = PREFETCH && (chunk + 1 < c_end) && (pn + 16 <= P.hpx);
+            if (!PREFETCH) load48_aligned(base + p0 * 3, w);
+            if (more) load48_aligned(base + pn * 3, wn);
             channel_sums(w, sum, sq);
             CellRun run;
             {

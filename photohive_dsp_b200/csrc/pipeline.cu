@@ -576,9 +576,12 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         CUDA_TRY(ctx, cudaMemsetAsync(records_dev + (size_t)first * lay.record_bytes, 0, lay.record_bytes * (size_t)n, st));
         phd_fe_plan(P, n);
         mark(&e0);
-        // front end and row FFT as one launch of role-switching CTAs where a fused kernel exists for the shape (fft.cu:
-        // k_front_rows) and the spectra of the whole group fit the spectrum buffer; two launches otherwise
-        static const bool fuse_enabled = !(getenv("PHD_FUSED") && atoi(getenv("PHD_FUSED")) == 0);
+        // PHD_FUSED=1: front end and row FFT as one launch of role-switching persistent CTAs (fft.cu: k_front_rows) where
+        // a fused kernel exists for the shape and the spectra of the whole group fit the spectrum buffer.  Records are
+        // byte-identical either way (tested); measured on B200 the fused launch is 5 % SLOWER than the two launches
+        // (45.1 vs 25.5 + 17.6 ms per 4096 images: both roles are bound by the same shared-memory pipe, and the register
+        // prefetch of the row stage had to go to fit 80 registers), so it is opt-in.  profiles/README.md has the numbers.
+        const bool fuse_enabled = getenv("PHD_FUSED") && atoi(getenv("PHD_FUSED")) != 0;
         const bool fused = fuse_enabled && fb >= n &&
                            phd_launch_front_rows(d_in, P, n, tab->tabs, tab->exc, shape->row, ctx->ws, st, &launches);
         ctx->last_fused = fused ? 1 : 0;

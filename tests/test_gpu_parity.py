@@ -339,6 +339,26 @@ def test_concurrent_callers_of_the_drop_in_entry_points(oracle):
         assert all(g == want[i] for g in got[i])
 
 
+@pytest.mark.parametrize("W,H", [(1920, 1080), (1280, 720), (2048, 1536), (640, 480)])
+def test_fused_front_end_and_row_fft_launch_gives_identical_records(ctx, oracle, W, H, monkeypatch):
+    """PHD_FUSED=1: front end + row FFT as one launch of role-switching persistent CTAs (fft.cu: k_front_rows).  Same
+    bytes as the two separate launches, and the call reports that it did run fused."""
+    torch = pytest.importorskip("torch")
+    n = 24
+    base = np.stack([oracle.generate(k % 3, 7000 + k, W, H) for k in range(6)])
+    imgs = torch.from_numpy(np.concatenate([base] * (n // 6))).cuda()
+    p = make_params()
+    lay = flat_layout(p, 0)
+    out = []
+    for fused in ("0", "1", "1"):
+        monkeypatch.setenv("PHD_FUSED", fused)
+        rec = np.empty((n, lay.record_bytes), np.uint8)
+        ctx.get_reports_raw(imgs.data_ptr(), n, W, H, W * H * 3, p, rec.ctypes.data)
+        assert ctx.last_fused() == (fused == "1")
+        out.append(rec)
+    assert (out[0] == out[1]).all() and (out[1] == out[2]).all()
+
+
 def test_pageable_and_pinned_host_batches_give_identical_records(ctx, oracle):
     """Pageable host input goes through the threaded pinned-slice uploader, pinned input through cudaMemcpy2DAsync."""
     torch = pytest.importorskip("torch")

@@ -201,10 +201,30 @@ PHD_API int phd_flat_get_layout(const phd_params* p, int max_boxes, phd_flat_lay
  * {top,bottom,left,right} (host memory); every image uses max_boxes boxes.
  * `records` receives n_images records of layout phd_flat_get_layout(p, max_boxes); it may be a
  * host or a device pointer.  Synchronous: returns after the records are written.
+ * Boxes must satisfy 0 <= top <= bottom <= height and 0 <= left <= right <= width (crop_pgm,
+ * src/image_processing.c:215-219, refuses anything else), at most 65535 per image; an empty box yields NaN as in
+ * the reference.  Otherwise PHD_E_BAD_PARAMS.
+ * ORDERING CONTRACT for device-resident input / output: the library works on its own non-blocking streams and does
+ * not know the caller's.  Whatever produced `rgb` (a kernel or a copy on another stream) must have COMPLETED before
+ * the call (synchronise that stream or its event first), and `rgb` / `records` must live on ctx's device.  On return
+ * all work of the call has completed, so the caller may reuse or free every buffer at once.
  */
 PHD_API int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_images, int width, int height,
                        size_t image_stride, const int* boxes, int max_boxes, const phd_params* p,
                        void* records);
+
+/*
+ * The same call on the GPUs of one box (images are independent, there is no exchange step
+ * and no collective).  ctxs[0..n_ctx-1] are contexts on DISTINCT devices; context g takes the contiguous range
+ * [g*n_images/n_ctx, (g+1)*n_images/n_ctx) of the batch on a host thread of its own and its device writes the
+ * records of that range straight into `records` -- the gather is the join of those threads.  `rgb` and `records` are
+ * HOST buffers (pinned buffers copy at the full PCIe rate; pageable ones go through the threaded staging uploader).
+ * Returns the first non-zero status of any range.  Replaces the per-image loop a caller of the reference's
+ * get_full_report_data (src/interface.c:20-94) would write over a photo collection.
+ */
+PHD_API int phd_get_reports_u8_multi(phd_context* const* ctxs, int n_ctx, const uint8_t* rgb, int n_images, int width,
+                             int height, size_t image_stride, const int* boxes, int max_boxes, const phd_params* p,
+                             void* records);
 
 /* Builds the drop-in, malloc-owned report from one flat record (free with free_full_report). */
 PHD_API Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_flat_layout* layout);

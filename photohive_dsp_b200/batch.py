@@ -247,6 +247,43 @@ class Context:
         return out
 
 
+class MultiContext:
+    """The GPUs of one box behind ONE call (phd_get_reports_u8_multi): one context per device, the batch is split into
+    contiguous ranges, every device writes its records into its range of one host array."""
+
+    def __init__(self, devices):
+        self.contexts = [Context(d) for d in devices]
+        self._arr = (C.c_void_p * len(self.contexts))(*[c._h for c in self.contexts])
+
+    def close(self):
+        for c in self.contexts:
+            c.close()
+
+    def get_reports_raw(self, rgb_ptr: int, n: int, width: int, height: int, stride: int, params: phd_params,
+                        records_ptr: int, boxes_ptr: int | None = None, max_boxes: int = 0) -> None:
+        rc = lib.phd_get_reports_u8_multi(self._arr, len(self.contexts), rgb_ptr, n, width, height, stride, boxes_ptr,
+                                          max_boxes, C.byref(params), records_ptr)
+        if rc != 0:
+            msgs = [(lib.phd_last_error(c._h) or b"").decode(errors="replace") for c in self.contexts]
+            raise PhotoHiveError(rc, "; ".join(m for m in msgs if m))
+
+    def get_reports(self, images: np.ndarray, boxes=None, params: phd_params | None = None, **param_overrides) -> BatchReports:
+        """images: uint8 [n,H,W,3] numpy array in HOST memory (pinned or pageable)."""
+        params = params or make_params(**param_overrides)
+        if not isinstance(images, np.ndarray):
+            raise TypeError("MultiContext takes host (numpy) batches; a device tensor belongs to one GPU")
+        ptr, n, H, W, stride, keep = _as_image_batch(images)
+        mb, bptr, bkeep = 0, None, None
+        if boxes is not None:
+            bkeep = np.ascontiguousarray(boxes, np.int32)
+            mb = bkeep.shape[1]
+            bptr = bkeep.ctypes.data_as(C.c_void_p) if mb > 0 else None
+        lay = flat_layout(params, mb)
+        raw = np.empty((n, lay.record_bytes), np.uint8)
+        self.get_reports_raw(ptr, n, W, H, stride, params, raw.ctypes.data_as(C.c_void_p), bptr, mb)
+        return view_records(raw, lay)
+
+
 def _as_image_batch(images, device=None):
     """-> (pointer, n, H, W, stride_bytes, keepalive)"""
     if isinstance(images, np.ndarray):

@@ -16,10 +16,10 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from .batch import BatchReports, Context, flat_layout, make_params
+from .batch import BatchReports, Context, PhotoHiveError, flat_layout, make_params
 from .lib import lib
 from .structures import Crop_Boundaries, Pixel_HSV
-from .utils import array_to_image_rgb, hsv_to_rgb, image_pgm_to_pillow, pil_image_to_image_rgb
+from .utils import array_to_image_rgb, hsv_to_rgb, image_pgm_to_pillow, pil_channels, pil_image_to_image_rgb
 
 _VERBOSE = bool(os.environ.get("PHD_VERBOSE"))
 _VIA_DOUBLES = bool(os.environ.get("PHD_GET_REPORT_VIA_DOUBLES"))  # force the reference's C entry point in get_report
@@ -176,9 +176,9 @@ def _report_from_bytes(image, crop, params):
     if isinstance(image, np.ndarray):
         arr = image
     else:
-        arr = np.asarray(image.convert("RGB") if image.mode != "RGB" else image)
+        arr = pil_channels(image)  # first three channels of np.array(image), like the reference (utils.py:30-33)
     if arr.ndim != 3 or arr.shape[2] != 3 or arr.dtype != np.uint8:
-        return None, 0, 0
+        return None, 0, 0          # 16-bit / float images: the planes of doubles go to the C entry point
     arr = np.ascontiguousarray(arr)
     height, width = arr.shape[:2]
     nb, barr = 0, None
@@ -201,8 +201,10 @@ def _report_from_bytes(image, crop, params):
         rec = np.empty((1, lay.record_bytes), np.uint8)
         ctx.get_reports_raw(arr.ctypes.data, 1, width, height, width * height * 3, p, rec.ctypes.data,
                             boxes_ptr=None if barr is None else barr.ctypes.data, max_boxes=nb)
-    except Exception:
-        return None, height, width  # let the C entry point print the reference's message
+    except PhotoHiveError as e:
+        if e.code in (1, 2):        # refused by the reference's pre-checks / bad parameters:
+            return None, height, width  # let the C entry point print the reference's message
+        raise                       # a CUDA fault or an unsupported size is not something to retry
     ptr = lib.phd_flat_to_full_report(rec.ctypes.data, ctypes.byref(lay))
     return (ptr if ptr else None), height, width
 

@@ -193,9 +193,25 @@ void fill_dev_params(DevParams& P, const phd_params& p, int W, int H, int max_bo
 }
 
 // Group centres exactly as initialize_octree computes them (src/color_quantization.c:58-98); host doubles, no FMA.
+// The caches of per-parameter tables and per-shape plans are bounded (a photo or crop collection with many sizes must
+// not grow device memory without limit): beyond the bound the least recently used entry is freed -- after the context's
+// stream has drained, since a queued kernel may still read it.
+constexpr size_t kMaxTables = 16, kMaxExcTables = 4, kMaxShapes = 32;
+
 int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
-    for (auto& t : ctx->tables)
-        if (same_params_for_tables(t.p, p)) { *out = &t; return PHD_OK; }
+    for (size_t i = 0; i < ctx->tables.size(); i++)
+        if (same_params_for_tables(ctx->tables[i].p, p)) {
+            if (i + 1 != ctx->tables.size()) std::rotate(ctx->tables.begin() + i, ctx->tables.begin() + i + 1, ctx->tables.end());
+            ctx->tables.back().p = p;  // the non-table parameters of this call
+            *out = &ctx->tables.back();
+            return PHD_OK;
+        }
+    if (ctx->tables.size() >= kMaxTables) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ParamTables& old = ctx->tables.front();
+        cudaFree(old.centres); cudaFree(old.sv_f); cudaFree(old.tabs);
+        ctx->tables.erase(ctx->tables.begin());
+    }
     const int hp = p.h_partitions, sp = p.s_partitions, vp = p.v_partitions;
     const int T = hp * sp * vp + vp + 1;
     std::vector<double> c(3 * (size_t)T, 0.0);
@@ -245,6 +261,19 @@ int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
     for (auto& e : ctx->exc_tables)
         if (e.first == hp) t.exc = e.second;
     if (!t.exc) {
+        if (ctx->exc_tables.size() >= kMaxExcTables) {
+            // drop the oldest code table no cached parameter set refers to any more
+            for (size_t i = 0; i < ctx->exc_tables.size(); i++) {
+                bool used = false;
+                for (auto& o : ctx->tables) used = used || o.exc == ctx->exc_tables[i].second;
+                if (!used) {
+                    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                    cudaFree(ctx->exc_tables[i].second);
+                    ctx->exc_tables.erase(ctx->exc_tables.begin() + i);
+                    break;
+                }
+            }
+        }
         CUDA_TRY(ctx, cudaMalloc(&new_exc, (size_t)1 << 24));
         t.exc = new_exc;
     }
@@ -265,8 +294,20 @@ int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
 }
 
 int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
-    for (auto& s : ctx->shapes)
-        if (s.W == W && s.H == H && s.nr == nr && s.na == na) { *out = &s; return PHD_OK; }
+    for (size_t i = 0; i < ctx->shapes.size(); i++) {
+        const ShapePlan& c = ctx->shapes[i];
+        if (c.W == W && c.H == H && c.nr == nr && c.na == na) {
+            if (i + 1 != ctx->shapes.size()) std::rotate(ctx->shapes.begin() + i, ctx->shapes.begin() + i + 1, ctx->shapes.end());
+            *out = &ctx->shapes.back();
+            return PHD_OK;
+        }
+    }
+    if (ctx->shapes.size() >= kMaxShapes) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ShapePlan& old = ctx->shapes.front();
+        cudaFree(old.tw_row); cudaFree(old.tw_col); cudaFree(old.binmap); cudaFree(old.bincount);
+        ctx->shapes.erase(ctx->shapes.begin());
+    }
     ShapePlan s;
     s.W = W; s.H = H; s.nr = nr; s.na = na;
     s.row.n = W; s.col.n = H;
@@ -772,6 +813,14 @@ int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_images, int w
     int rc = check_params(ctx, p, max_boxes);
     if (rc != PHD_OK) return rc;
     if (max_boxes > 0 && !boxes) return fail(ctx, PHD_E_BAD_PARAMS, "max_boxes > 0 but boxes is NULL");
+    if (max_boxes > 65535) return fail(ctx, PHD_E_BAD_PARAMS, "more than 65535 boxes per image");
+    // crop_pgm (src/image_processing.c:215-219) refuses boxes outside the image (the reference then dereferences NULL);
+    // inverted boxes make it allocate a negative size.  Empty boxes (top == bottom) are served like the reference: NaN.
+    for (long long i = 0; i < (long long)n_images * max_boxes; i++) {
+        const int t = boxes[4 * i], b = boxes[4 * i + 1], l = boxes[4 * i + 2], r = boxes[4 * i + 3];
+        if (t < 0 || l < 0 || b > height || r > width || t > b || l > r)
+            return fail(ctx, PHD_E_BAD_PARAMS, "Error: crop boundaries outside of image boundaries.");
+    }
     char why[256];
     if (reference_rejects(width, height, why, sizeof(why))) return fail(ctx, PHD_E_REJECTED, why);
     if (image_stride < (size_t)width * height * 3) return fail(ctx, PHD_E_BAD_PARAMS, "image_stride smaller than one image");
@@ -788,7 +837,12 @@ int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_images, int w
     }
     rc = run_pipeline(ctx, rgb, in_dev, n_images, width, height, image_stride, boxes, max_boxes, *p, rec_dev, lay);
     if (rc != PHD_OK) {
+        // nothing of this context may still read the caller's buffers once the error is returned
         cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (int t = 0; t < phd_context::kUpThreads; t++)
+            if (ctx->up_stream[t]) cudaStreamSynchronize(ctx->up_stream[t]);
+        cudaGetLastError();
         return rc;
     }
     if (!out_dev)
@@ -797,6 +851,40 @@ int phd_get_reports_u8(phd_context* ctx, const uint8_t* rgb, int n_images, int w
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     return collect_timing(ctx);
+}
+
+// images are independent, so a batch shards over the GPUs of one box with no exchange step.
+// One host thread per context (device); thread g takes the contiguous range [g*B/G, (g+1)*B/G) of the batch and its
+// device writes the records straight into that range of the caller's array -- the gather is the join.
+int phd_get_reports_u8_multi(phd_context* const* ctxs, int n_ctx, const uint8_t* rgb, int n_images, int width, int height,
+                             size_t image_stride, const int* boxes, int max_boxes, const phd_params* p, void* records) {
+    if (!ctxs || n_ctx <= 0 || !rgb || !records || n_images <= 0 || !p) return PHD_E_BAD_PARAMS;
+    for (int g = 0; g < n_ctx; g++) {
+        if (!ctxs[g]) return PHD_E_BAD_PARAMS;
+        for (int o = 0; o < g; o++)
+            if (ctxs[o] == ctxs[g]) return PHD_E_BAD_PARAMS;  // one range per context
+    }
+    if (is_device_pointer(rgb) || is_device_pointer(records)) {
+        fprintf(stderr, "photohive_dsp: phd_get_reports_u8_multi takes HOST buffers (a device buffer belongs to one GPU)\n");
+        return PHD_E_BAD_PARAMS;
+    }
+    phd_flat_layout lay;
+    if (phd_flat_get_layout(p, max_boxes, &lay) != PHD_OK) return PHD_E_BAD_PARAMS;
+    std::vector<int> rcs(n_ctx, PHD_OK);
+    auto work = [&](int g) {
+        const long long lo = (long long)n_images * g / n_ctx, hi = (long long)n_images * (g + 1) / n_ctx;
+        if (hi <= lo) return;
+        rcs[g] = phd_get_reports_u8(ctxs[g], rgb + (size_t)lo * image_stride, (int)(hi - lo), width, height, image_stride,
+                                    boxes ? boxes + (size_t)lo * max_boxes * 4 : nullptr, max_boxes, p,
+                                    (unsigned char*)records + (size_t)lo * lay.record_bytes);
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < n_ctx; g++) pool.emplace_back(work, g);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (int g = 0; g < n_ctx; g++)
+        if (rcs[g] != PHD_OK) return rcs[g];
+    return PHD_OK;
 }
 
 int phd_last_timing(const phd_context* ctx, float ms[8]) {
@@ -824,46 +912,74 @@ Full_Report_Data* phd_flat_to_full_report(const void* record, const phd_flat_lay
     const double* bins = (const double*)(rec + lay->off_blur_bins);
     const double* sharp = (const double*)(rec + lay->off_sharpness);
 
-    Full_Report_Data* r = (Full_Report_Data*)malloc(sizeof(Full_Report_Data));
+    // every block is checked; on exhaustion whatever was built is released through the same path the caller would use
+    Full_Report_Data* r = (Full_Report_Data*)calloc(1, sizeof(Full_Report_Data));
+    if (!r) return NULL;
+    bool ok = true;
     r->rgb_stats = (RGB_Statistics*)calloc(1, sizeof(RGB_Statistics));
-    r->rgb_stats->Br = h->rgb_stats[0]; r->rgb_stats->Bg = h->rgb_stats[1]; r->rgb_stats->Bb = h->rgb_stats[2];
-    r->rgb_stats->Cr = h->rgb_stats[3]; r->rgb_stats->Cg = h->rgb_stats[4]; r->rgb_stats->Cb = h->rgb_stats[5];
+    if (r->rgb_stats) {
+        r->rgb_stats->Br = h->rgb_stats[0]; r->rgb_stats->Bg = h->rgb_stats[1]; r->rgb_stats->Bb = h->rgb_stats[2];
+        r->rgb_stats->Cr = h->rgb_stats[3]; r->rgb_stats->Cg = h->rgb_stats[4]; r->rgb_stats->Cb = h->rgb_stats[5];
+    } else ok = false;
     r->average_saturation = h->average_saturation;
 
-    Color_Palette* cp = (Color_Palette*)malloc(sizeof(Color_Palette));
-    cp->N = h->palette_n;
-    cp->averages = (Pixel_HSV*)calloc(cp->N > 0 ? cp->N : 1, sizeof(Pixel_HSV));
-    cp->percentages = (Pixel*)calloc(cp->N > 0 ? cp->N : 1, sizeof(Pixel));
-    for (int i = 0; i < cp->N; i++) {
-        cp->averages[i].parent_id = pid[i];
-        cp->averages[i].h = hsv[3 * i]; cp->averages[i].s = hsv[3 * i + 1]; cp->averages[i].v = hsv[3 * i + 2];
-        cp->percentages[i] = pct[i];
-    }
+    Color_Palette* cp = (Color_Palette*)calloc(1, sizeof(Color_Palette));
     r->color_palette = cp;
+    if (cp) {
+        cp->N = h->palette_n;
+        cp->averages = (Pixel_HSV*)calloc(cp->N > 0 ? cp->N : 1, sizeof(Pixel_HSV));
+        cp->percentages = (Pixel*)calloc(cp->N > 0 ? cp->N : 1, sizeof(Pixel));
+        if (cp->averages && cp->percentages) {
+            for (int i = 0; i < cp->N; i++) {
+                cp->averages[i].parent_id = pid[i];
+                cp->averages[i].h = hsv[3 * i]; cp->averages[i].s = hsv[3 * i + 1]; cp->averages[i].v = hsv[3 * i + 2];
+                cp->percentages[i] = pct[i];
+            }
+        } else ok = false;
+    } else ok = false;
 
-    Blur_Profile* bp = (Blur_Profile*)malloc(sizeof(Blur_Profile));
-    bp->num_angle_bins = h->num_angle_bins; bp->num_radius_bins = h->num_radius_bins;
-    bp->angle_bin_size = h->angle_bin_size; bp->radius_bin_size = h->radius_bin_size;
-    bp->bins = (Bin**)malloc(sizeof(Bin*) * bp->num_angle_bins);
-    for (int a = 0; a < bp->num_angle_bins; a++) {
-        bp->bins[a] = (Bin*)malloc(sizeof(Bin) * bp->num_radius_bins);
-        memcpy(bp->bins[a], bins + (size_t)a * bp->num_radius_bins, sizeof(Bin) * bp->num_radius_bins);
-    }
+    Blur_Profile* bp = (Blur_Profile*)calloc(1, sizeof(Blur_Profile));
     r->blur_profile = bp;
+    if (bp) {
+        bp->num_radius_bins = h->num_radius_bins;
+        bp->angle_bin_size = h->angle_bin_size; bp->radius_bin_size = h->radius_bin_size;
+        bp->bins = (Bin**)calloc(h->num_angle_bins > 0 ? h->num_angle_bins : 1, sizeof(Bin*));
+        if (bp->bins) {
+            bp->num_angle_bins = h->num_angle_bins;  // free_full_report walks this many rows (NULL rows are fine for free)
+            for (int a = 0; a < bp->num_angle_bins; a++) {
+                bp->bins[a] = (Bin*)malloc(sizeof(Bin) * (bp->num_radius_bins > 0 ? bp->num_radius_bins : 1));
+                if (!bp->bins[a]) { ok = false; continue; }
+                memcpy(bp->bins[a], bins + (size_t)a * bp->num_radius_bins, sizeof(Bin) * bp->num_radius_bins);
+            }
+        } else ok = false;
+    } else ok = false;
 
     Blur_Vector_Group* bv = (Blur_Vector_Group*)calloc(1, sizeof(Blur_Vector_Group));
-    bv->len_vectors = 10;
-    bv->blur_vectors = (Blur_Vector*)calloc(10, sizeof(Blur_Vector));
-    for (int k = 0; k < 10; k++) { bv->blur_vectors[k].angle = h->blur_vec_angle[k]; bv->blur_vectors[k].magnitude = h->blur_vec_mag[k]; }
     r->blur_vectors = bv;
+    if (bv) {
+        bv->blur_vectors = (Blur_Vector*)calloc(10, sizeof(Blur_Vector));
+        if (bv->blur_vectors) {
+            bv->len_vectors = 10;
+            for (int k = 0; k < 10; k++) { bv->blur_vectors[k].angle = h->blur_vec_angle[k]; bv->blur_vectors[k].magnitude = h->blur_vec_mag[k]; }
+        } else ok = false;
+    } else ok = false;
 
     r->sharpness = NULL;
     if (h->n_sharpness >= 0) {
-        Sharpnesses* s = (Sharpnesses*)malloc(sizeof(Sharpnesses));
-        s->N = h->n_sharpness;
-        s->sharpness = (Pixel*)calloc(s->N > 0 ? s->N : 1, sizeof(Pixel));
-        for (int i = 0; i < s->N; i++) s->sharpness[i] = sharp[i];
+        Sharpnesses* s = (Sharpnesses*)calloc(1, sizeof(Sharpnesses));
         r->sharpness = s;
+        if (s) {
+            s->sharpness = (Pixel*)calloc(h->n_sharpness > 0 ? h->n_sharpness : 1, sizeof(Pixel));
+            if (s->sharpness) {
+                s->N = h->n_sharpness;
+                for (int i = 0; i < s->N; i++) s->sharpness[i] = sharp[i];
+            } else ok = false;
+        } else ok = false;
+    }
+    if (!ok) {
+        fprintf(stderr, "photohive_dsp: out of host memory while building the report\n");
+        free_full_report(&r);
+        return NULL;
     }
     return r;
 }
@@ -1007,7 +1123,10 @@ Full_Report_Data* get_full_report_data(Image_RGB* image, Crop_Boundaries* crop, 
     const int W = image->width, H = image->height;
     const long long npx = (long long)W * H;
     const int nb = crop ? crop->N : 0;
-    if (check_params(ctx, &p, nb) != PHD_OK) return NULL;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);  // check_params writes the context's error buffer
+        if (check_params(ctx, &p, nb) != PHD_OK) return NULL;
+    }
     std::vector<int> boxes((size_t)(nb > 0 ? nb : 1) * 4);
     for (int i = 0; i < nb; i++) {
         boxes[4 * i] = crop->top[i]; boxes[4 * i + 1] = crop->bottom[i];

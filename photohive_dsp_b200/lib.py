@@ -50,6 +50,9 @@ lib.phd_flat_get_layout.argtypes = [C.POINTER(phd_params), C.c_int, C.POINTER(ph
 lib.phd_get_reports_u8.restype = C.c_int
 lib.phd_get_reports_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
                                    C.c_int, C.POINTER(phd_params), C.c_void_p]
+lib.phd_get_reports_u8_multi.restype = C.c_int
+lib.phd_get_reports_u8_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                         C.c_void_p, C.c_int, C.POINTER(phd_params), C.c_void_p]
 lib.phd_flat_to_full_report.restype = C.POINTER(Full_Report_Data)
 lib.phd_flat_to_full_report.argtypes = [C.c_void_p, C.POINTER(phd_flat_layout)]
 lib.phd_last_timing.restype = C.c_int
@@ -71,7 +74,7 @@ lib.phd_debug_group_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
 
 EXPORTED = ["get_full_report_data", "free_full_report", "get_blur_profile_visual", "phd_default_params",
             "phd_context_create", "phd_context_destroy", "phd_last_error", "phd_flat_get_layout",
-            "phd_get_reports_u8", "phd_flat_to_full_report", "phd_last_timing", "phd_last_stage_launches", "phd_last_fused",
+            "phd_get_reports_u8", "phd_get_reports_u8_multi", "phd_flat_to_full_report", "phd_last_timing", "phd_last_stage_launches", "phd_last_fused",
             "phd_debug_group_sweep",
             "phd_debug_group_sweep_exact",
             "phd_debug_bin_map", "phd_debug_power_spectrum", "phd_debug_group_counts"]

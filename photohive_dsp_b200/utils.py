@@ -19,12 +19,21 @@ def hsv_to_rgb(h, s, v):
     return int((r + base) * 255), int((g + base) * 255), int((b + base) * 255)
 
 
+def pil_channels(pil_image) -> np.ndarray:
+    """The array the reference works on (utils.py:30-33): ``np.array(pil_image)``, first three channels.  No mode
+    conversion: RGBA drops alpha, CMYK / YCbCr / LAB pass their first three channels through as the reference does, and a
+    single-channel image ('L', 'P', 'I;16' ...) raises the same IndexError (the array is 2-D)."""
+    arr = np.array(pil_image)
+    arr[:, :, 2]  # IndexError for 2-D (single channel) and two-channel arrays, exactly where the reference raises it
+    return arr[:, :, 0:3]
+
+
 def pil_image_to_image_rgb(pil_image):
-    """PIL image -> Image_RGB of three contiguous float64 planes holding k/255.0 (utils.py:30-46).
+    """PIL image -> Image_RGB of three contiguous float64 planes holding value/255.0 (utils.py:30-46).
     The planes are parked on the PIL object so they outlive the C call."""
     width, height = pil_image.size
-    arr = np.asarray(pil_image.convert("RGB") if pil_image.mode != "RGB" else pil_image)
-    planes = [np.ascontiguousarray(arr[:, :, c].astype(np.float64) / 255.0).ravel() for c in range(3)]
+    arr = pil_channels(pil_image)
+    planes = [np.ascontiguousarray(arr[:, :, c] / 255.0, dtype=np.float64).ravel() for c in range(3)]
     ptrs = [p.ctypes.data_as(_dp) for p in planes]
     pil_image._phd_planes = planes
     pil_image.r_ctypes, pil_image.g_ctypes, pil_image.b_ctypes = ptrs

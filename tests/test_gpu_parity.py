@@ -191,6 +191,65 @@ def test_two_devices_in_one_process(ctx, oracle):
     assert np.array_equal(a.raw, b.raw) and np.array_equal(a.raw, c.raw)
 
 
+def test_multi_gpu_entry_point_of_the_c_abi(ctx, oracle):
+    """phd_get_reports_u8_multi: contiguous ranges of one host batch on every visible GPU, records gathered by the join.
+    On a one-GPU box the call still runs (one range); with two or more the ranges land on different devices."""
+    import torch
+    from photohive_dsp_b200.batch import MultiContext
+    ndev = torch.cuda.device_count()
+    imgs = np.stack([oracle.generate(k % 3, 800 + k, 800, 600) for k in range(7)])   # 7: uneven ranges
+    boxes = np.array([[[0, 300, 0, 400], [100, 600, 300, 800]]] * 7, np.int32)
+    want = ctx.get_reports(imgs, boxes=boxes)
+    for devices in ([0], list(range(ndev)), list(range(ndev))[::-1]):
+        mc = MultiContext(devices)
+        try:
+            got = mc.get_reports(imgs, boxes=boxes)
+            pinned = torch.from_numpy(imgs).pin_memory()
+            lay = got.layout
+            rec = np.empty((7, lay.record_bytes), np.uint8)
+            mc.get_reports_raw(pinned.data_ptr(), 7, 800, 600, 800 * 600 * 3, make_params(), rec.ctypes.data,
+                               boxes.ctypes.data, 2)
+        finally:
+            mc.close()
+        assert np.array_equal(got.raw, want.raw) and np.array_equal(rec, want.raw)
+    # device buffers and repeated contexts are refused
+    from photohive_dsp_b200.batch import PhotoHiveError
+    mc = MultiContext([0])
+    try:
+        with pytest.raises(PhotoHiveError):
+            mc.get_reports_raw(torch.from_numpy(imgs).cuda().data_ptr(), 7, 800, 600, 800 * 600 * 3, make_params(),
+                               rec.ctypes.data)
+    finally:
+        mc.close()
+
+
+def test_batch_entry_point_validates_boxes(ctx, oracle):
+    """Boxes outside the image or inverted are refused (the reference's crop_pgm returns NULL and is then dereferenced);
+    an empty box gives NaN like the reference, not an error."""
+    from photohive_dsp_b200.batch import PhotoHiveError
+    img = oracle.generate(1, 3, 640, 480)[None]
+    for bad in ([0, 481, 0, 10], [-1, 10, 0, 10], [0, 10, 0, 641], [20, 10, 0, 10], [0, 10, 30, 20]):
+        with pytest.raises(PhotoHiveError) as e:
+            ctx.get_reports(img, boxes=np.array([[bad]], np.int32))
+        assert e.value.code == 2
+    b = ctx.get_reports(img, boxes=np.array([[[5, 5, 0, 10], [0, 480, 0, 640]]], np.int32))
+    assert np.isnan(b.sharpness[0, 0]) and np.isfinite(b.sharpness[0, 1])
+
+
+def test_pil_modes_follow_the_reference_conversion(oracle):
+    """get_report takes the first three channels of np.array(pil_image) like the reference (utils.py:30-33): RGBA drops
+    alpha, CMYK passes C, M, Y through, single-channel modes raise IndexError -- no silent .convert('RGB')."""
+    from PIL import Image
+    import photohive_dsp_b200 as P
+    arr = oracle.generate(2, 21, 640, 480)
+    rgb = P.get_report(Image.fromarray(arr, "RGB")).to_json()
+    rgba = np.concatenate([arr, np.full((480, 640, 1), 77, np.uint8)], -1)
+    assert P.get_report(Image.fromarray(rgba, "RGBA")).to_json() == rgb
+    assert P.get_report(Image.fromarray(rgba, "CMYK")).to_json() == rgb      # C, M, Y bytes taken as they are
+    with pytest.raises(IndexError):
+        P.get_report(Image.fromarray(arr[:, :, 0], "L"))
+
+
 def test_edge_images(ctx, oracle):
     """Flat, black, white and two-colour images: empty spectrum, single group, max==1 clamps."""
     H, W = 400, 560

@@ -250,17 +250,23 @@ def main():
             "gpu_launches": 0}))
         return 0
 
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 meanwhile (NCCL's version banner, the
+    # reference's printf in the cpu_baseline leg) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from photohive_dsp_b200.batch import Context, MultiContext, flat_layout, make_params
     from tools.synth import Generator
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}))
+        os.write(real_stdout, (json.dumps({"error": "no CUDA device: the product path has no CPU fallback"}) + "\n").encode())
         return 2
     n_local = args.gpus if in_process else 1           # GPUs this process drives
     if in_process and torch.cuda.device_count() < args.gpus:
-        print(json.dumps({"error": f"--gpus {args.gpus} but only {torch.cuda.device_count()} visible"}))
+        os.write(real_stdout, (json.dumps({"error": f"--gpus {args.gpus} but only {torch.cuda.device_count()} visible"}) + "\n").encode())
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -494,7 +500,8 @@ def main():
                 line["cpu_baseline"], _ = cpu_arm(images_per_core=3 if w * h <= 2_100_000 else 1, cfg_id=args.config)
             except Exception as e:  # the baseline is a reported figure; never let it hide the measurement
                 line["cpu_baseline"] = {"error": str(e)[:200]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -222,7 +222,9 @@ template <bool PK> struct Radix<25, PK> : Composite<5, 5, PK> {};
 
 // Per-pass twiddle tables of the compile-time plans: pass i (radix R, stride S, M = N/R butterflies) reads
 // twp[off_i + (j-1)*M + b] = exp(-2 pi i * (b - b % S) * j / N), j = 1..R-1 -- consecutive lanes read consecutive
-// entries (the plain table indexed by pps*j scatters a warp over up to 2*j cache lines).
+// entries (the plain table indexed by pps*j scatters a warp over up to 2*j cache lines).  Only M/S of a pass's bases
+// differ, but a compact table indexed by b/S measured SLOWER (rows +19 %, columns +30 % at 1080p): one entry per
+// butterfly it stays.
 template <int N, int R0, int R1, int R2, int R3>
 struct PlanT {
     static constexpr int off0 = 0;
@@ -317,7 +319,7 @@ __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* _
         const int b = idx - col * m;
         const float2* a = in + col * bstride;
         float2* y = out + col * bstride;
-        const int q = b % s;
+        const int bs = b / s, q = b - bs * s;
         const int pps = b - q;
         float2 x[R];
 #pragma unroll
@@ -341,7 +343,7 @@ __device__ void pass_rt_prime(int r, const float2* __restrict__ in, float2* __re
         const int col = rest / m, b = rest - col * m;
         const float2* a = in + col * bstride;
         float2* y = out + col * bstride;
-        const int q = b % s;
+        const int bs = b / s, q = b - bs * s;
         const int pps = b - q;
         float2 acc = a[b];
         int e = 0;  // (j * k) % r, stepped
@@ -461,6 +463,8 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
         const uint8_t* base = img_base + (size_t)(2 * PAIRS * q) * N * 3;
         const uint4* s0 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair) * N * 3 + (size_t)seg * 48);
         const uint4* s1 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair + 1) * N * 3 + (size_t)seg * 48);
+        // plain cached loads: the three 16-byte pieces of neighbouring threads share 128-byte lines, and loads that
+        // bypass L1 (ld.global.nc.L1::no_allocate) measured 20 % slower for the whole kernel
         a0 = __ldg(s0); b0 = __ldg(s0 + 1); c0 = __ldg(s0 + 2);
         a1 = __ldg(s1); b1 = __ldg(s1 + 1); c1 = __ldg(s1 + 2);
     };

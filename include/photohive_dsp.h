@@ -115,8 +115,10 @@ typedef struct Full_Report_Data {
  * Replaces src/interface.c:20-94 (declared src/interface.h:16-23).
  * Returns a malloc-owned report, or NULL (+ a message on stderr) when the reference would
  * (src/utilities.c:64-87: NULL image or planes, a side < 350, > 120 M pixels, aspect outside
- * [1/5, 5]) or when the GPU path cannot serve the request (no CUDA device, unsupported
- * transform length, image values that are not k/255 -- see DESIGN.md "Scope").
+ * [1/5, 5]) or when the GPU path cannot serve the request (no CUDA device, an image side beyond
+ * the shared-memory FFT -- see DESIGN.md "Limits").
+ * Planes holding k/255.0 (8-bit images, what utils.py:30-37 produces) take the integer pipeline; any other doubles
+ * (16-bit images, create_test_rgb of src/debug.c:53 ...) take a two-pass FP64 route (csrc/f64path.cu).
  * The input image and boxes are not modified and stay owned by the caller.
  */
 PHD_API Full_Report_Data* get_full_report_data(Image_RGB* image, Crop_Boundaries* salient_characters,
@@ -183,7 +185,7 @@ enum {
     PHD_E_NO_DEVICE = 3,
     PHD_E_CUDA = 4,
     PHD_E_UNSUPPORTED = 5, /* e.g. a transform length with a prime factor the FFT does not cover */
-    PHD_E_NOT_8BIT = 6
+    PHD_E_NOT_8BIT = 6     /* no longer produced: non-8-bit planes are served by the FP64 route of get_full_report_data */
 };
 
 typedef struct phd_context phd_context; /* one per CUDA device; owns streams, plans, workspaces */

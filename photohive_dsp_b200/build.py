@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "PhotoHive_DSP_lib")   # same relative location as the reference (lib.py:21)
 LIB = os.path.join(OUT_DIR, "libreport_data.so")
 OBJ_DIR = os.path.join(PKG, "build")
-SOURCES = ["frontend.cu", "palette_select.cu", "fft.cu", "sharpness.cu", "finalize.cu", "pipeline.cu"]
+SOURCES = ["frontend.cu", "palette_select.cu", "fft.cu", "sharpness.cu", "finalize.cu", "f64path.cu", "pipeline.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -576,9 +576,12 @@ __global__ void __launch_bounds__(256, 3) k_front_rows(const uint8_t* __restrict
 // after the bias) and land in the Hp padding of the transposed spectrum.
 // N > 0: the width is the compile-time length N with plan R0 R1 R2 (widths that have a plan but not the 16-pixel
 // granularity of k_rows_t, e.g. 1080-pixel portrait rows): same staging, compile-time passes, THREADS threads.
+// gray32 != nullptr: the input is a plane of floats (general-input route: (gray - 0.5) * 255000 of one image) instead
+// of packed bytes.
 template <int NP, int N = 0, int R0 = 1, int R1 = 1, int R2 = 1, int THREADS = 512>
 __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
-                                                              float2* __restrict__ specT) {
+                                                              float2* __restrict__ specT,
+                                                              const float* __restrict__ gray32 = nullptr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = N > 0 ? N : P.W;
     float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [NP][W]
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
     const int vw = gran == 0 ? 16 : ((gran & 7) == 0 ? 8 : ((gran & 3) == 0 ? 4 : 1));
     for (int q = blockIdx.x; q < ngroups; q += gridDim.x) {
         __syncthreads();  // the previous group's output loop has finished reading bufB
-        for (int r = 0; r < 2 * NP; r++) {
+        for (int r = 0; r < 2 * NP && !gray32; r++) {
             const int row = 2 * NP * q + r;
             unsigned char* dst = raw + (size_t)r * row_bytes;
             if (row >= P.H) continue;
@@ -622,9 +625,15 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
             for (int h = 0; h < 2; h++) {
                 const int row = 2 * NP * q + 2 * pair + h;
                 const unsigned char* px = raw + (size_t)(2 * pair + h) * row_bytes + 3 * x;
-                g[h] = row < P.H ? 299 * (int)px[0] + 587 * (int)px[1] + 114 * (int)px[2] - PHD_GRAY_BIAS : 0;
+                g[h] = (row < P.H && !gray32) ? 299 * (int)px[0] + 587 * (int)px[1] + 114 * (int)px[2] - PHD_GRAY_BIAS : 0;
             }
-            bufA[idx] = make_float2((float)g[0], (float)g[1]);
+            float2 v = make_float2((float)g[0], (float)g[1]);
+            if (gray32) {
+                const int row = 2 * NP * q + 2 * pair;
+                v.x = row < P.H ? __ldg(gray32 + (size_t)row * W + x) : 0.f;
+                v.y = row + 1 < P.H ? __ldg(gray32 + (size_t)(row + 1) * W + x) : 0.f;
+            }
+            bufA[idx] = v;
         }
         __syncthreads();
         const float2* z;
@@ -695,6 +704,10 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
 // sums and stored so that the common power arithmetic below reproduces it.
 __device__ __forceinline__ void cols_fix_dc(const DevParams& P, const ImageAcc* __restrict__ iacc, int img, float2* res00) {
     const ImageAcc a = iacc[img];
+    if (a.dc_valid) {  // general-input route: computed from the doubles (f64path.cu)
+        *res00 = make_float2((float)(a.dc * 255000.0), 0.f);
+        return;
+    }
     const double np = (double)P.npx;
     const double avg = ((double)a.sum[0] / 255.0 / np + (double)a.sum[1] / 255.0 / np + (double)a.sum[2] / 255.0 / np) / 3.0;
     const double gsum = (299.0 * (double)a.sum[0] + 587.0 * (double)a.sum[1] + 114.0 * (double)a.sum[2]) / 255000.0;
@@ -1169,6 +1182,22 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
         if (one_pair) k_rows_generic<1><<<dim3(gx, nimg), 512, smem, st>>>(rgb, P, row, specT);
         else k_rows_generic<2><<<dim3(gx, nimg), smem > 72 * 1024 ? 512 : kRowThreads, smem, st>>>(rgb, P, row, specT);
     }
+    return 0;
+}
+
+// Row transform of ONE image given as a plane of floats (general-input route): the runtime-radix kernel serves every width.
+int phd_launch_fft_rows_gray(const float* gray32, const DevParams& P, const FftPlan& row, float2* specT, cudaStream_t st,
+                             int* launches) {
+    *launches += 1;
+    size_t smem = (size_t)P.W * 4 * sizeof(float2);
+    const bool one_pair = smem > 200 * 1024;
+    if (one_pair) smem /= 2;
+    if (smem > 200 * 1024) return 1;
+    PHD_ALLOW_SMEM((k_rows_generic<1>), 200 * 1024);
+    PHD_ALLOW_SMEM((k_rows_generic<2>), 200 * 1024);
+    const int gx = rows_generic_grid(smem, P.Hp / (one_pair ? 2 : 4), 1);
+    if (one_pair) k_rows_generic<1><<<dim3(gx, 1), 512, smem, st>>>(nullptr, P, row, specT, gray32);
+    else k_rows_generic<2><<<dim3(gx, 1), smem > 72 * 1024 ? 512 : kRowThreads, smem, st>>>(nullptr, P, row, specT, gray32);
     return 0;
 }
 

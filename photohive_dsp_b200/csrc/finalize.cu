@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
                                                   const u32* __restrict__ maxpow, const SharpAcc* __restrict__ sharp,
                                                   const int* __restrict__ boxes, const int* __restrict__ tie_groups,
                                                   const long long* __restrict__ dropped, phd_flat_layout lay,
-                                                  unsigned char* __restrict__ records) {
+                                                  unsigned char* __restrict__ records,
+                                                  const double* __restrict__ f64_acc, const double* __restrict__ f64_slots,
+                                                  const double* __restrict__ f64_sharp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* bins = reinterpret_cast<double*>(smem_raw);  // [nbins]
     const int img = blockIdx.x, tid = threadIdx.x, T = P.T;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
 
     // --- partly accepted tie groups: fold the pixels k_palette_ties accepted into their parent's sums ---
     {
-        const int nt = tie_n[img];
+        const int nt = f64_slots ? 0 : tie_n[img];  // the general-input route has already added its tie pixels
         const u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
         for (int k = tid; k < nt; k += blockDim.x) {
             const int g = tie_list[(size_t)img * T + k];
@@ -78,11 +80,17 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
             }
             const double off = 180.0 - centres[pid];
             const double inv = 1.0 / (double)A.cnt;
-            h = (double)A.t_sum * (1.0 / (double)(1 << PHD_T_SHIFT)) * inv - off;
+            if (f64_slots) {  // general-input route: FP64 sums of v, s and the wrapped hue
+                h = f64_slots[4 * j + 2] * inv - off;
+                s = f64_slots[4 * j + 1] * inv;
+                v = f64_slots[4 * j] * inv;
+            } else {
+                h = (double)A.t_sum * (1.0 / (double)(1 << PHD_T_SHIFT)) * inv - off;
+                s = (double)A.s_sum * (1.0 / (double)(1 << PHD_S_SHIFT)) * inv;
+                v = ((double)(A.summax - 255ull * A.n255) / 255.0 + (double)A.n255 * 0.999999) * inv;
+            }
             if (h < 0) h += 360;
             else if (h > 360) h -= 360;
-            s = (double)A.s_sum * (1.0 / (double)(1 << PHD_S_SHIFT)) * inv;
-            v = ((double)(A.summax - 255ull * A.n255) / 255.0 + (double)A.n255 * 0.999999) * inv;
             pct = (double)A.cnt * inv_total;
         }
         out_hsv[3 * j] = h; out_hsv[3 * j + 1] = s; out_hsv[3 * j + 2] = v;
@@ -107,7 +115,11 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
         const int* bx = boxes + ((size_t)img * P.max_boxes + k) * 4;
         const int w = bx[3] - bx[2], h = bx[1] - bx[0];
         double r = nan("");
-        if (w > 0 && h > 0 && bx[2] >= 0 && bx[0] >= 0 && bx[3] <= P.W && bx[1] <= P.H) {
+        if (f64_sharp && w > 0 && h > 0) {
+            const double dn = (double)w * (double)h;
+            const double avg = f64_sharp[2 * k] / dn;
+            r = (f64_sharp[2 * k + 1] / dn - avg * avg) / avg;
+        } else if (w > 0 && h > 0 && bx[2] >= 0 && bx[0] >= 0 && bx[3] <= P.W && bx[1] <= P.H) {
             const SharpAcc S = sharp[(size_t)img * P.max_boxes + k];
             const long long n = (long long)w * h;
             // n*S2 - S1^2 exactly, then var = that / (n^2 * 255000^2), avg = S1 / (n * 255000)
@@ -123,14 +135,20 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
     __syncthreads();
 
     if (tid == 0) {
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < 3 && f64_acc; c++) {
+            const double mean = f64_acc[c] / np;
+            head->rgb_stats[c] = mean;
+            head->rgb_stats[3 + c] = sqrt(fmax(f64_acc[3 + c] / np - mean * mean, 0.0));
+        }
+        for (int c = 0; c < 3 && !f64_acc; c++) {
             const double mean = (double)a.sum[c] / 255.0 / np;
             const unsigned __int128 num = (unsigned __int128)a.sumsq[c] * (unsigned __int128)P.npx -
                                           (unsigned __int128)a.sum[c] * (unsigned __int128)a.sum[c];
             head->rgb_stats[c] = mean;
             head->rgb_stats[3 + c] = sqrt(u128_to_double(num) / (np * np * 65025.0));
         }
-        head->average_saturation = (double)a.s_sum * (1.0 / (double)(1 << PHD_S_SHIFT)) / (double)P.hpx;
+        head->average_saturation = f64_acc ? f64_acc[7] / (double)P.hpx
+                                           : (double)a.s_sum * (1.0 / (double)(1 << PHD_S_SHIFT)) / (double)P.hpx;
         head->max_power = maxp;
         head->dropped_pixels = dropped[img];
         head->palette_n = N;
@@ -189,11 +207,13 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
 }  // namespace
 
 void phd_launch_finalize(const DevParams& P, int nimg, const double* centres, const int* bincount, Workspace& ws,
-                         const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches) {
+                         const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches,
+                         const F64Work* f64) {
     const size_t smem = ((size_t)P.nbins + 2 * (size_t)P.na) * sizeof(double);
     PHD_ALLOW_SMEM((k_finalize), 200 * 1024);
     k_finalize<<<nimg, 256, smem, st>>>(P, centres, bincount, ws.iacc, ws.pal_n, ws.parent_ids, ws.sacc, ws.plan,
                                         ws.tie_list, ws.tie_n, ws.cells_tie, ws.binsum,
-                                        ws.maxpow, ws.sharp, ws.boxes, ws.tie_groups, ws.dropped, lay, records_dev);
+                                        ws.maxpow, ws.sharp, ws.boxes, ws.tie_groups, ws.dropped, lay, records_dev,
+                                        f64 ? f64->acc : nullptr, f64 ? f64->slots : nullptr, f64 ? f64->sharp : nullptr);
     *launches += 1;
 }

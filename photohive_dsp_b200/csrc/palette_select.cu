@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                                                         u64* __restrict__ cells_tie_g,
                                                         const u32* __restrict__ span32,
                                                         const u64* __restrict__ span64, u32* __restrict__ work,
-                                                        u32* __restrict__ work_n) {
+                                                        u32* __restrict__ work_n, const int from_hist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = P.T, tid = threadIdx.x, img = blockIdx.x;
     int* n = reinterpret_cast<int*>(smem_raw);       // [T] pixel counts
@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     for (int w = tid; w < nbw; w += blockDim.x) cbits[w] = 0;
     if (tid == 0) { sh_ssum = 0; sh_nscan = 0; }
     __syncthreads();
-    {
+    if (from_hist) {  // general-input route: the totals come from k_f64_classify; no cells, no saturation sum here
+        for (int g = tid; g < T; g += blockDim.x) n[g] = (int)hist[(size_t)img * T + g];
+    } else {
         u64 ssum = 0;
         for (int pair = tid; pair < P.ncls * P.hp; pair += blockDim.x) {
             u64 c = 0;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
         if ((tid & 31) == 0 && ssum) atomicAdd(&sh_ssum, ssum);
     }
     __syncthreads();
-    if (tid == 0) iacc[img].s_sum = sh_ssum;
+    if (tid == 0 && !from_hist) iacc[img].s_sum = sh_ssum;
 
     for (int g = tid; g < T; g += blockDim.x) {
         const int c = n[g];
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
         }
         plan_g[(size_t)img * T + g] = gp;
         // everything that joins a parent as a whole: fold its cells into the parent's sums
-        if (gp.mode == 1) {
+        if (gp.mode == 1 && !from_hist) {
             const GroupSums S = phd_reduce_group(cells, P, g, gh[ids[gp.slot]]);
             SlotAcc* a = sacc + (size_t)img * T + gp.slot;
             if (S.summax) atomicAdd(&a->summax, S.summax);
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                 gp->clast = clast;
                 if (clast >= 0) atomicOr(&cbits[clast >> 5], 1u << (clast & 31));
             }
+            if (from_hist) continue;  // the general-input route accumulates pixels, not cells
             // its tie cells: the sums of the wholly accepted spans (zero when there is none)
             u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
             int c0, nc;
@@ -363,11 +366,12 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
 }  // namespace
 
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
-                               cudaStream_t st, int* launches) {
+                               cudaStream_t st, int* launches, bool from_hist) {
     const size_t smem = (size_t)P.T * 11 * sizeof(int) + (size_t)((P.nchunks + 31) / 32) * sizeof(u32);
     PHD_ALLOW_SMEM((k_palette_select), 200 * 1024);
     k_palette_select<<<nimg, 256, smem, st>>>(P, centres, sv_f, ws.cells, ws.counts_chunk, ws.plan, ws.pal_n,
                                               ws.parent_ids, ws.tie_list, ws.tie_n, ws.tie_groups, ws.dropped, ws.sacc,
-                                              ws.hist, ws.iacc, ws.cells_tie, ws.span32, ws.span64, ws.work, ws.work_n);
+                                              ws.hist, ws.iacc, ws.cells_tie, ws.span32, ws.span64, ws.work, ws.work_n,
+                                              from_hist ? 1 : 0);
     *launches += 1;
 }

@@ -79,7 +79,17 @@ struct ImageAcc {
     u64 sum[3];    // sum of k per channel
     u64 sumsq[3];  // sum of k^2 per channel
     u64 s_sum;     // sum of s * 2^PHD_S_SHIFT over the HSV image
+    u64 dc_valid;  // general-input route (f64path.cu): `dc` holds X[0,0] of the reference's transform
+    double dc;
     u64 pad;
+};
+
+// Accumulators of the general-input (planes of arbitrary doubles) route, one image per call (f64path.cu).
+struct F64Work {
+    double* acc;     // [10]  sum r,g,b; sum of squares r,g,b; sum gray; sum of saturations; (Br+Bg+Bb)/3; unused
+    double* slots;   // [T][4]  per parent slot: sum v, sum s, sum wrapped hue
+    double* sharp;   // [max_boxes][2]  sum f, sum f^2
+    float* gray32;   // [npx]  (gray - average) * 255000, the row transform's input
 };
 
 struct SharpAcc {
@@ -150,8 +160,9 @@ static inline size_t phd_fe_max_spans(const DevParams& P0, int cap) {
 // ---- launchers (each in its own .cu) --------------------------------------------------------
 void phd_launch_pixels(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                        const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches);
+// from_hist: the group totals are already in ws.hist (general-input route); the cells are not consulted
 void phd_launch_palette_select(const DevParams& P, int nimg, const double* centres, const float* sv_f, Workspace& ws,
-                               cudaStream_t st, int* launches);
+                               cudaStream_t st, int* launches, bool from_hist = false);
 void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                              const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches);
 void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const unsigned char* exc, bool fast,
@@ -175,7 +186,17 @@ void phd_launch_bin_map(int W, int H, int Hp, int nr, int na, u16* map_dev, int*
 
 void phd_launch_sharpness(const uint8_t* rgb, const DevParams& P, int nimg, int max_w, int max_h, Workspace& ws,
                           cudaStream_t st, int* launches);
+// f64: accumulators of the general-input route (one image) instead of the integer ones, or nullptr
 void phd_launch_finalize(const DevParams& P, int nimg, const double* centres, const int* bincount, Workspace& ws,
-                         const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches);
+                         const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches,
+                         const F64Work* f64 = nullptr);
 
 size_t phd_fft_cols_smem(const DevParams& P, int* tile_cols);
+
+// general-input route (f64path.cu)
+void phd_launch_f64_front(const double* planes, const DevParams& P, F64Work& fw, Workspace& ws, cudaStream_t st, int* launches);
+void phd_launch_f64_accumulate(const double* planes, const DevParams& P, const double* centres, F64Work& fw, Workspace& ws,
+                               cudaStream_t st, int* launches);
+size_t phd_f64_accumulate_smem(const DevParams& P);
+int phd_launch_fft_rows_gray(const float* gray32, const DevParams& P, const FftPlan& row, float2* specT, cudaStream_t st,
+                             int* launches);

@@ -66,6 +66,12 @@ struct phd_context {
     unsigned char* d_u8 = nullptr;
     size_t d_u8_bytes = 0;
     int* d_flag = nullptr;
+    // general-input route (f64path.cu): accumulators (one zeroed allocation) and the float gray plane
+    F64Work f64{};
+    unsigned char* f64_zero = nullptr;
+    size_t f64_zero_bytes = 0;
+    unsigned char* f64_gray = nullptr;
+    size_t f64_gray_bytes = 0;
     // uploader threads of the drop-in call: each owns a stream, two pinned slices and their "slice free again" events
     static constexpr int kUpThreads = 8;
     static constexpr size_t kUpSlice = 2u << 20;
@@ -666,6 +672,60 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
     return PHD_OK;
 }
 
+// The general-input route: ONE image given as three device planes of arbitrary doubles (see f64path.cu).  Same stage
+// order as run_pipeline; the palette is done in two FP64 passes around the unchanged parent selection, the FFT reads a
+// float gray plane.
+int run_pipeline_f64(phd_context* ctx, const double* planes_dev, int W, int H, const int* boxes_host, int max_boxes,
+                     const phd_params& p, unsigned char* records_dev, const phd_flat_layout& lay) {
+    DevParams P;
+    fill_dev_params(P, p, W, H, max_boxes, 0, 0);
+    if (P.dw < 1 || P.dh < 1) return fail(ctx, PHD_E_BAD_PARAMS, "downsample_rate leaves no pixels");
+    ShapePlan* shape;
+    ParamTables* tab;
+    int rc;
+    if ((rc = get_shape(ctx, W, H, P.nr, P.na, &shape)) != PHD_OK) return rc;
+    if ((rc = get_tables(ctx, p, &tab)) != PHD_OK) return rc;
+    if ((rc = ensure_workspace(ctx, P, 1, 1)) != PHD_OK) return rc;
+    int tc;
+    if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024 ||
+        phd_f64_accumulate_smem(P) > 200 * 1024)
+        return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
+    P.cpp = P.nchunks;  // one span: the tie path of this route ranks pixels itself, nothing is folded from span sums
+    P.nspans = 1;
+    const size_t nb1 = max_boxes > 0 ? max_boxes : 1;
+    const size_t zbytes = sizeof(double) * (10 + 4 * (size_t)P.T + 2 * nb1);
+    if ((rc = ensure_bytes(ctx, &ctx->f64_zero, &ctx->f64_zero_bytes, zbytes)) != PHD_OK) return rc;
+    if ((rc = ensure_bytes(ctx, &ctx->f64_gray, &ctx->f64_gray_bytes, sizeof(float) * (size_t)P.npx)) != PHD_OK) return rc;
+    F64Work& fw = ctx->f64;
+    fw.acc = reinterpret_cast<double*>(ctx->f64_zero);
+    fw.slots = fw.acc + 10;
+    fw.sharp = fw.slots + 4 * (size_t)P.T;
+    fw.gray32 = reinterpret_cast<float*>(ctx->f64_gray);
+
+    cudaStream_t st = ctx->stream;
+    ctx->spans.clear();
+    ctx->events_used = 0;
+    for (int i = 0; i < 8; i++) ctx->last_stage_launches[i] = 0;
+    int launches = 0;
+    if (max_boxes > 0)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.boxes, boxes_host, sizeof(int) * 4 * (size_t)max_boxes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->f64_zero, 0, zbytes, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(records_dev, 0, lay.record_bytes, st));
+    phd_launch_f64_front(planes_dev, P, fw, ctx->ws, st, &launches);
+    phd_launch_palette_select(P, 1, tab->centres, tab->sv_f, ctx->ws, st, &launches, true);
+    phd_launch_f64_accumulate(planes_dev, P, tab->centres, fw, ctx->ws, st, &launches);
+    if (phd_launch_fft_rows_gray(fw.gray32, P, shape->row, ctx->ws.spec, st, &launches))
+        return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
+    if (phd_launch_fft_cols_blur(P, 1, shape->col, ctx->ws.spec, shape->binmap, ctx->ws, nullptr, st, &launches))
+        return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
+    phd_launch_finalize(P, 1, tab->centres, shape->bincount, ctx->ws, lay, records_dev, st, &launches, &fw);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->last_launches = launches;
+    ctx->last_fused = 0;
+    return PHD_OK;
+}
+
 int collect_timing(phd_context* ctx) {
     for (int i = 0; i < 8; i++) ctx->last_ms[i] = 0.f;
     for (size_t i = 0; i + 2 < ctx->spans.size(); i += 3) {
@@ -768,6 +828,7 @@ void phd_context_destroy(phd_context* ctx) {
     cudaFree(ctx->ws_zero); cudaFree(ctx->d_rgb); cudaFree(ctx->d_records);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_u8); cudaFree(ctx->d_flag);
+    cudaFree(ctx->f64_zero); cudaFree(ctx->f64_gray);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     for (int t = 0; t < phd_context::kUpThreads; t++) {
         if (ctx->up_stream[t]) cudaStreamDestroy(ctx->up_stream[t]);
@@ -1184,14 +1245,22 @@ Full_Report_Data* get_full_report_data(Image_RGB* image, Crop_Boundaries* crop, 
             return NULL;
         }
     }
-    if (flag) {
-        fprintf(stderr, "photohive_dsp: image values are not of the form k/255 (8-bit); this build only serves 8-bit images\n");
-        return NULL;
-    }
     phd_flat_layout lay;
     phd_flat_get_layout(&p, nb, &lay);
     std::vector<unsigned char> rec(lay.record_bytes);
-    const int rc = phd_get_reports_u8(ctx, ctx->d_u8, 1, W, H, stride, nb > 0 ? boxes.data() : NULL, nb, &p, rec.data());
+    int rc;
+    if (flag) {
+        // values that are not k/255: the general-input route on the planes already on the device (f64path.cu)
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->err[0] = 0;
+        rc = ensure_bytes(ctx, &ctx->d_records, &ctx->d_records_bytes, lay.record_bytes);
+        if (rc == PHD_OK) rc = run_pipeline_f64(ctx, ctx->d_planes, W, H, nb > 0 ? boxes.data() : NULL, nb, p, ctx->d_records, lay);
+        if (rc == PHD_OK && cudaMemcpyAsync(rec.data(), ctx->d_records, lay.record_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            rc = PHD_E_CUDA;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == PHD_OK) rc = PHD_E_CUDA;
+    } else {
+        rc = phd_get_reports_u8(ctx, ctx->d_u8, 1, W, H, stride, nb > 0 ? boxes.data() : NULL, nb, &p, rec.data());
+    }
     if (rc != PHD_OK) return NULL;
     result = phd_flat_to_full_report(rec.data(), &lay);
     if (result && !crop && result->sharpness) {  // unreachable (n_sharpness = -1 when nb == 0), kept for clarity

@@ -43,13 +43,24 @@ class Golden:
         self.meta = json.loads(bytes(z["meta"]).decode())
 
     def names(self, max_pixels=None):
-        return [n for n, m in self.meta.items() if max_pixels is None or m["W"] * m["H"] <= max_pixels]
+        return [n for n, m in self.meta.items() if "planes" not in m and (max_pixels is None or m["W"] * m["H"] <= max_pixels)]
+
+    def plane_names(self):
+        return [n for n, m in self.meta.items() if "planes" in m]
 
     def image(self, oracle, name):
         m = self.meta[name]
         img = oracle.generate(m["kind"], m["seed"], m["W"], m["H"])
         assert zlib.crc32(img.tobytes()) == m["crc32"], "synthetic generator no longer reproduces the fixture input"
         return img
+
+    def planes(self, name):
+        """Three float64 planes of a general-input (not k/255) fixture, regenerated and CRC-guarded like the images."""
+        from parity import planes_for
+        m = self.meta[name]
+        planes = planes_for(m["planes"], m["seed"], m["W"], m["H"])
+        assert zlib.crc32(np.stack(planes).tobytes()) == m["crc32"], "plane generator no longer reproduces the fixture input"
+        return planes
 
     def field(self, name, key):
         k = f"{name}/{key}"

@@ -15,7 +15,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import binding  # noqa: E402
+from parity import planes_for  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden.npz")
 
@@ -41,27 +43,49 @@ CASES = {
 }
 
 
+# name -> (plane kind, seed, W, H, params overrides, with boxes?)
+PLANE_CASES = {
+    "f64_test_rgb": ("test_rgb", 0, 400, 360, {}, False),
+    "f64_random": ("random", 11, 480, 360, {}, True),
+    "f64_random_ties": ("random", 12, 480, 360, dict(linked_list_size=40, coverage_thresh=0.6, downsample_rate=2), True),
+    "f64_k65535": ("k65535", 13, 401, 357, dict(h_partitions=12, s_partitions=3, v_partitions=4), False),
+}
+
+
+def store_report(store, name, r):
+    store[f"{name}/rgb_stats"] = r.rgb_stats
+    store[f"{name}/average_saturation"] = np.array(r.average_saturation)
+    store[f"{name}/palette_hsv"] = r.palette_hsv
+    store[f"{name}/palette_pct"] = r.palette_pct
+    store[f"{name}/blur_bins"] = r.blur_bins
+    store[f"{name}/ints"] = np.array([r.angle_bin_size, r.radius_bin_size], np.int32)
+    store[f"{name}/blur_vec_angle"] = r.blur_vec_angle
+    store[f"{name}/blur_vec_mag"] = r.blur_vec_mag
+    if r.sharpness is not None:
+        store[f"{name}/sharpness"] = r.sharpness
+
+
 def main():
     binding.build(ref=True)
     orc = binding.Oracle()
     ref = binding.Reference(0)
     store, meta = {}, {}
+    for name, (kind, seed, W, H, kw, with_boxes) in PLANE_CASES.items():
+        planes = planes_for(kind, seed, W, H)
+        bx = boxes_for(W, H) if with_boxes else None
+        r = ref.report(None, binding.make_params(**kw), boxes=bx, planes=planes)
+        assert r is not None, name
+        crc = zlib.crc32(np.stack(planes).tobytes())
+        meta[name] = dict(planes=kind, seed=seed, W=W, H=H, params=kw, boxes=bx, crc32=crc)
+        store_report(store, name, r)
+        print(name, "N=%d sum%%=%.12f" % (len(r.palette_pct), r.palette_pct.sum()))
     for name, (kind, seed, W, H, kw, with_boxes) in CASES.items():
         img = orc.generate(kind, seed, W, H)
         bx = boxes_for(W, H) if with_boxes else None
         r = ref.report(img, binding.make_params(**kw), boxes=bx)
         assert r is not None, name
         meta[name] = dict(kind=kind, seed=seed, W=W, H=H, params=kw, boxes=bx, crc32=zlib.crc32(img.tobytes()))
-        store[f"{name}/rgb_stats"] = r.rgb_stats
-        store[f"{name}/average_saturation"] = np.array(r.average_saturation)
-        store[f"{name}/palette_hsv"] = r.palette_hsv
-        store[f"{name}/palette_pct"] = r.palette_pct
-        store[f"{name}/blur_bins"] = r.blur_bins
-        store[f"{name}/ints"] = np.array([r.angle_bin_size, r.radius_bin_size], np.int32)
-        store[f"{name}/blur_vec_angle"] = r.blur_vec_angle
-        store[f"{name}/blur_vec_mag"] = r.blur_vec_mag
-        if r.sharpness is not None:
-            store[f"{name}/sharpness"] = r.sharpness
+        store_report(store, name, r)
         print(name, "N=%d sum%%=%.12f" % (len(r.palette_pct), r.palette_pct.sum()))
     store["meta"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
     np.savez_compressed(OUT, **store)

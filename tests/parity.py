@@ -47,6 +47,22 @@ def rel_err(a, b, floor=1e-300):
     return np.where(np.isnan(e), np.inf, e)
 
 
+def planes_for(kind, seed, W, H):
+    """Planes of doubles that are NOT k/255 (the general-input route): 'test_rgb' is the reference's own
+    create_test_rgb (src/debug.c:53-60), 'random' numpy's PCG64 stream (platform independent), 'k65535' 16-bit values."""
+    n = W * H
+    if kind == "test_rgb":
+        i = np.arange(n, dtype=np.float64)
+        return tuple((1.0 / (i * m + 1.0)).reshape(H, W) for m in (1.0, 2.0, 4.0))
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        return tuple(rng.random((H, W)) for _ in range(3))
+    if kind == "k65535":
+        return tuple(rng.integers(0, 65536, (H, W)).astype(np.float64) / 65535.0 for _ in range(3))
+    raise ValueError(kind)
+
+
+
 def fft_error_report(pw, ref):
     """pw: FP32 power spectrum of the product path, ref: float64 power spectrum (same shape).  Returns a dict with the
     per-coefficient relative error of the magnitude |X| (median, p99, max, and max over the coefficients above 1e-3 of

@@ -447,13 +447,47 @@ def test_batch_json_export_equals_single_report_json(ctx, oracle):
         assert single == dicts[i] == json.loads(batch.to_json(i, 480, 640))
 
 
-def test_non_8bit_image_is_refused_loudly(capfd):
+def _drop_in_on_planes(planes, W, H, params, boxes):
     from oracle import binding
     from photohive_dsp_b200 import lib as L
     lib = binding.bind_entry_points(C.CDLL(L.lib_path))
-    planes = tuple(np.full(400 * 400, 0.1234567, np.float64) for _ in range(3))
-    assert not binding.call_entry_point(lib, planes, 400, 400, omake(), None)
-    assert "8-bit" in capfd.readouterr().err
+    flat = tuple(np.ascontiguousarray(p, np.float64).ravel() for p in planes)
+    rp = binding.call_entry_point(lib, flat, W, H, params, boxes)
+    assert rp, "get_full_report_data returned NULL"
+    got = binding.unpack_full_report(rp)
+    lib.free_full_report(C.byref(rp))
+    return got
+
+
+# palette hue of the general-input route: FP64 sums, no 2^-20 quantisation -- but the blur bins still come from the FP32 FFT
+@pytest.mark.parametrize("name", ["f64_test_rgb", "f64_random", "f64_random_ties", "f64_k65535"])
+def test_general_double_planes_match_reference_golden(oracle, golden, name):
+    """images whose values are not k/255 -- accepted by the reference (src/image_processing.c:372-417),
+    refused by round 1 -- go through the FP64 two-pass route (f64path.cu) and match the unmodified reference's outputs."""
+    m = golden.meta[name]
+    got = _drop_in_on_planes(golden.planes(name), m["W"], m["H"], omake(**m["params"]), m["boxes"])
+    assert_report_close(got, golden_report(golden, name), name)
+
+
+@pytest.mark.parametrize("W,H,kw,nbox", [
+    (1920, 1080, {}, 2),
+    (800, 600, dict(linked_list_size=16, coverage_thresh=0.5), 0),            # many tie groups with dropped pixels
+    (752, 502, dict(downsample_rate=3, h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99), 1),
+])
+def test_general_double_planes_match_oracle(oracle, W, H, kw, nbox):
+    rng = np.random.default_rng(W + H)
+    # smooth ramps plus noise: values of every magnitude, many exactly equal channel pairs (delta == 0, max == g ...)
+    y, x = np.mgrid[0:H, 0:W]
+    planes = [np.clip((x / W) * 0.7 + rng.random((H, W)) * 0.3, 0, 1), np.clip((y / H) * 0.9 + rng.random((H, W)) * 0.1, 0, 1),
+              np.clip(rng.random((H, W)) ** 2, 0, 1)]
+    planes[1][: H // 8] = planes[0][: H // 8]      # r == g rows
+    planes[2][H // 8: H // 4] = 0.0                # a zero channel: delta == max
+    planes[0][-H // 8:] = planes[1][-H // 8:] = planes[2][-H // 8:] = 1.0   # max == 1 -> the 0.999999 clamps
+    boxes = [dict(top=H * i // 8, bottom=H * i // 8 + H // 4, left=W * i // 8, right=W * i // 8 + W // 4) for i in range(nbox)] or None
+    want = oracle.report(None, omake(**kw), boxes=boxes, nthreads=8, planes=tuple(planes))
+    got = _drop_in_on_planes(planes, W, H, omake(**kw), boxes)
+    assert_report_close(got, want, f"doubles {W}x{H} {kw}")
+    assert len(got.palette_pct) == len(want.palette_pct)
 
 
 @pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160), (6000, 4000), (1280, 720), (2560, 1440), (1024, 768),

@@ -30,6 +30,17 @@ def test_oracle_matches_reference_golden(oracle, golden, name):
     assert np.max(np.abs(got.blur_bins - want.blur_bins)) < 1e-11
 
 
+@pytest.mark.parametrize("name", ["f64_test_rgb", "f64_random", "f64_random_ties", "f64_k65535"])
+def test_oracle_matches_reference_golden_on_general_doubles(oracle, golden, name):
+    """Planes of doubles that are not k/255 (create_test_rgb of src/debug.c:53, random doubles, 16-bit values): the
+    oracle's double-precision path against the fixtures the unmodified reference wrote."""
+    m = golden.meta[name]
+    got = oracle.report(None, make_params(**m["params"]), boxes=m["boxes"], nthreads=4, planes=golden.planes(name))
+    want = golden_report(golden, name)
+    assert_report_close(got, want, name)
+    assert np.max(np.abs(got.blur_bins - want.blur_bins)) < 1e-11
+
+
 def test_survey_known_answers(golden):
     """SURVEY.md B.3 values (reference at -O0, defaults, 1920x1080) are what the fixtures hold."""
     g1 = golden_report(golden, "g1_1080p")

@@ -27,6 +27,7 @@
 // about a millisecond per image -- but arbitrary crops are served rather than refused).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "fft_tables.cuh"
 #include "frontend_walk.cuh"
@@ -360,36 +361,96 @@ __device__ float2* fft_run_rt(const FftPlan& pl, float2* bufA, float2* bufB, int
     float2* a = bufA;
     float2* b = bufB;
     int s = 1;
+    const int len = pl.m > 0 ? pl.m : pl.n;  // a Bluestein plan carries the radix plan of its padded length
     for (int f = 0; f < pl.nfac; f++) {
         const int r = pl.fac[f];
         const float2* twp = pl.twp + pl.twp_off[f];
         switch (r) {
-            case 2: pass_rt<2>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 3: pass_rt<3>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 4: pass_rt<4>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 5: pass_rt<5>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 6: pass_rt<6>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 7: pass_rt<7>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 8: pass_rt<8>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 9: pass_rt<9>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 10: pass_rt<10>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 11: pass_rt<11>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 12: pass_rt<12>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 13: pass_rt<13>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 15: pass_rt<15>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 16: pass_rt<16>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 17: pass_rt<17>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 18: pass_rt<18>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 19: pass_rt<19>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 21: pass_rt<21>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            case 25: pass_rt<25>(a, b, pl.n, s, twp, nbatch, bstride); break;
-            default: pass_rt_prime(r, a, b, pl.n, s, pl.tw, twp, nbatch, bstride); break;
+            case 2: pass_rt<2>(a, b, len, s, twp, nbatch, bstride); break;
+            case 3: pass_rt<3>(a, b, len, s, twp, nbatch, bstride); break;
+            case 4: pass_rt<4>(a, b, len, s, twp, nbatch, bstride); break;
+            case 5: pass_rt<5>(a, b, len, s, twp, nbatch, bstride); break;
+            case 6: pass_rt<6>(a, b, len, s, twp, nbatch, bstride); break;
+            case 7: pass_rt<7>(a, b, len, s, twp, nbatch, bstride); break;
+            case 8: pass_rt<8>(a, b, len, s, twp, nbatch, bstride); break;
+            case 9: pass_rt<9>(a, b, len, s, twp, nbatch, bstride); break;
+            case 10: pass_rt<10>(a, b, len, s, twp, nbatch, bstride); break;
+            case 11: pass_rt<11>(a, b, len, s, twp, nbatch, bstride); break;
+            case 12: pass_rt<12>(a, b, len, s, twp, nbatch, bstride); break;
+            case 13: pass_rt<13>(a, b, len, s, twp, nbatch, bstride); break;
+            case 15: pass_rt<15>(a, b, len, s, twp, nbatch, bstride); break;
+            case 16: pass_rt<16>(a, b, len, s, twp, nbatch, bstride); break;
+            case 17: pass_rt<17>(a, b, len, s, twp, nbatch, bstride); break;
+            case 18: pass_rt<18>(a, b, len, s, twp, nbatch, bstride); break;
+            case 19: pass_rt<19>(a, b, len, s, twp, nbatch, bstride); break;
+            case 21: pass_rt<21>(a, b, len, s, twp, nbatch, bstride); break;
+            case 25: pass_rt<25>(a, b, len, s, twp, nbatch, bstride); break;
+            default: pass_rt_prime(r, a, b, len, s, pl.tw, twp, nbatch, bstride); break;
         }
         __syncthreads();
         s *= r;
         float2* t = a; a = b; b = t;
     }
     return a;
+}
+
+// Bluestein (chirp-z) for lengths with a large prime factor: X[k] = w[k] * sum_j (x[j] w[j]) conj(w)[k-j] with
+// w[k] = exp(-i pi k^2 / n), the sum being a circular convolution of length m >= 2n-1 done with two transforms of the
+// small-radix length m (the inverse one as conj(FFT(conj(.)))).  O(m log m) per sequence instead of the O(n p) of the
+// direct pass over a prime factor p (src/fft_processing.c:34 leaves this choice to FFTW, which does the same).
+// In: nbatch sequences of n values at stride bstride (>= m) in bufA.  Returns the buffer holding the n results.
+__device__ float2* fft_run_blue(const FftPlan& pl, float2* bufA, float2* bufB, int nbatch, int bstride) {
+    const int n = pl.n, m = pl.m;
+    for (int idx = threadIdx.x; idx < nbatch * m; idx += blockDim.x) {
+        const int col = idx / m, k = idx - col * m;
+        float2* p = bufA + col * bstride + k;
+        *p = k < n ? cmulf<false>(*p, __ldg(&pl.chirp[k])) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2* r = fft_run_rt(pl, bufA, bufB, nbatch, bstride);
+    float2* other = (r == bufA) ? bufB : bufA;
+    for (int idx = threadIdx.x; idx < nbatch * m; idx += blockDim.x) {
+        const int col = idx / m, k = idx - col * m;
+        float2* p = r + col * bstride + k;
+        const float2 v = cmulf<false>(*p, __ldg(&pl.bhat[k]));
+        *p = make_float2(v.x, -v.y);
+    }
+    __syncthreads();
+    float2* r2 = fft_run_rt(pl, r, other, nbatch, bstride);
+    for (int idx = threadIdx.x; idx < nbatch * n; idx += blockDim.x) {
+        const int col = idx / n, k = idx - col * n;
+        float2* p = r2 + col * bstride + k;
+        const float2 v = *p;
+        *p = cmulf<false>(make_float2(v.x, -v.y), __ldg(&pl.chirp[k]));
+    }
+    __syncthreads();
+    return r2;
+}
+
+// chirp[k] = exp(-i pi k^2 / n); bhat = (1/m) * DFT_m of the conjugate chirp laid out circularly (index -j at m - j).
+// Evaluated straight from the definition in double precision, once per shape.
+__global__ void k_bluestein_tables(float2* __restrict__ chirp, float2* __restrict__ bhat, int n, int m) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        double sn, cs;
+        sincospi((double)(((long long)k * k) % (2LL * n)) / (double)n, &sn, &cs);
+        chirp[k] = make_float2((float)cs, (float)(-sn));
+    }
+    if (k < m) {
+        double re = 0, im = 0;
+        for (int j = -(n - 1); j < n; j++) {
+            // exp(+i pi j^2 / n) * exp(-2 pi i j k / m): one angle, both parts reduced exactly in integers
+            const double a1 = (double)(((long long)j * j) % (2LL * n)) / (double)n;
+            long long jk = ((long long)j * k) % m;
+            if (jk < 0) jk += m;
+            const double a2 = 2.0 * (double)jk / (double)m;
+            double sn, cs;
+            sincospi(a1 - a2, &sn, &cs);
+            re += cs;
+            im += sn;
+        }
+        bhat[k] = make_float2((float)(re / m), (float)(im / m));
+    }
 }
 
 __global__ void k_twiddles(float2* tw, int n) {
@@ -584,8 +645,9 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
                                                               const float* __restrict__ gray32 = nullptr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = N > 0 ? N : P.W;
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [NP][W]
-    float2* bufB = bufA + NP * W;                        // [NP][W]; first holds the raw bytes of the rows (6 W NP <= 8 W NP)
+    const int L = (N == 0 && pl.m > 0) ? pl.m : W;       // sequence stride: the padded length of a Bluestein plan
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);  // [NP][L]
+    float2* bufB = bufA + NP * L;                        // [NP][L]; first holds the raw bytes of the rows (6 W NP <= 8 L NP)
     unsigned char* raw = reinterpret_cast<unsigned char*>(bufB);
     const int img = blockIdx.y;
     const int ngroups = P.Hp / (2 * NP);
@@ -633,7 +695,7 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
                 v.x = row < P.H ? __ldg(gray32 + (size_t)row * W + x) : 0.f;
                 v.y = row + 1 < P.H ? __ldg(gray32 + (size_t)(row + 1) * W + x) : 0.f;
             }
-            bufA[idx] = v;
+            bufA[pair * L + x] = v;
         }
         __syncthreads();
         const float2* z;
@@ -641,7 +703,7 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
             z = fft_run_t<N, R0, R1, R2, 1, false, THREADS / NP, false>(bufA, bufB, pl.twp, NP, N, N);
             __syncthreads();
         } else {
-            z = fft_run_rt(pl, bufA, bufB, NP, W);
+            z = pl.m > 0 ? fft_run_blue(pl, bufA, bufB, NP, L) : fft_run_rt(pl, bufA, bufB, NP, W);
         }
         float2* out = specT + (size_t)img * P.fw * P.Hp + 2 * NP * q;
         for (int k = threadIdx.x; k < P.fw; k += blockDim.x) {
@@ -649,7 +711,7 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
             float4 v[NP];
 #pragma unroll
             for (int pr = 0; pr < NP; pr++) {
-                const float2 zk = z[pr * W + k], zc = z[pr * W + kc];
+                const float2 zk = z[pr * L + k], zc = z[pr * L + kc];
                 v[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
             }
             float* o = reinterpret_cast<float*>(out + (size_t)k * P.Hp);
@@ -873,9 +935,10 @@ __global__ void __launch_bounds__(kColThreads, 2) k_cols_generic(DevParams P, Ff
                                                               float* __restrict__ power_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Hp = P.Hp;
+    const int L = pl.m > 0 ? pl.m : Hp;  // column stride in shared memory: the padded length of a Bluestein plan
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
-    float2* bufB = bufA + (size_t)TC * Hp;
-    u32* bin_lo = reinterpret_cast<u32*>(bufB + (size_t)TC * Hp);
+    float2* bufB = bufA + (size_t)TC * L;
+    u32* bin_lo = reinterpret_cast<u32*>(bufB + (size_t)TC * L);
     u32* bin_hi = bin_lo + P.nbins;
     __shared__ float sh_max[kColThreads / 32];
 
@@ -885,15 +948,18 @@ __global__ void __launch_bounds__(kColThreads, 2) k_cols_generic(DevParams P, Ff
     const float2* src = specT + ((size_t)img * P.fw + x0) * Hp;
     if (!WRITE_POWER)
         for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
-    for (int idx = threadIdx.x; idx < ncol * Hp; idx += blockDim.x) bufA[idx] = src[idx];
+    for (int idx = threadIdx.x; idx < ncol * Hp; idx += blockDim.x) {
+        const int c = idx / Hp, k = idx - c * Hp;
+        bufA[c * L + k] = src[idx];
+    }
     __syncthreads();
-    float2* res = fft_run_rt(pl, bufA, bufB, ncol, Hp);
+    float2* res = pl.m > 0 ? fft_run_blue(pl, bufA, bufB, ncol, L) : fft_run_rt(pl, bufA, bufB, ncol, L);
     if (WRITE_POWER) {
-        cols_write_power(P, img, x0, ncol, res, Hp, power_out);
+        cols_write_power(P, img, x0, ncol, res, L, power_out);
         return;
     }
     if (x0 == 0 && threadIdx.x == 0) cols_fix_dc(P, iacc, img, res);  // thread 0 also owns point (0,0) below
-    const float mymax = cols_accumulate<8, 0>(P.H, ncol, res, Hp, binmapT + (size_t)x0 * Hp, Hp, bin_lo, bin_hi, 0.f);
+    const float mymax = cols_accumulate<8, 0>(P.H, ncol, res, L, binmapT + (size_t)x0 * Hp, Hp, bin_lo, bin_hi, 0.f);
     __syncthreads();
     cols_flush(P, img, mymax, bin_lo, bin_hi, sh_max, binsum, maxpow);
 }
@@ -1054,9 +1120,40 @@ int phd_fft_plan_factors(int n, int* fac, int* nfac) {
     return 0;
 }
 
+// Plan of length n.  A length whose largest prime factor exceeds kBlueMinPrime is transformed by Bluestein through the
+// smallest 2^a 3^b 5^c >= 2n-1, provided that padded length still fits the shared-memory kernels; everything else (and
+// longer sides) keeps the direct radix plan with its O(p^2) pass for odd primes.
+int phd_fft_make_plan(int n, FftPlan* pl) {
+    constexpr int kBlueMinPrime = 40, kBlueMaxLen = 11000;
+    memset(pl, 0, sizeof(*pl));
+    pl->n = n;
+    int r4[4];
+    int largest = 1, rem = n;
+    for (int q = 2; q * q <= rem; q++)
+        while (rem % q == 0) { largest = q > largest ? q : largest; rem /= q; }
+    if (rem > largest) largest = rem;
+    if (!special_radices(n, r4) && largest > kBlueMinPrime) {
+        int best = 0;
+        for (long long a = 1; a <= kBlueMaxLen; a *= 2)
+            for (long long b = a; b <= kBlueMaxLen; b *= 3)
+                for (long long c = b; c <= kBlueMaxLen; c *= 5)
+                    if (c >= 2LL * n - 1 && (best == 0 || c < best)) best = (int)c;
+        if (best > 0) {
+            pl->m = best;
+            return phd_fft_plan_factors(best, pl->fac, &pl->nfac);
+        }
+    }
+    return phd_fft_plan_factors(n, pl->fac, &pl->nfac);
+}
+
+void phd_fft_fill_bluestein(float2* chirp_dev, float2* bhat_dev, int n, int m, cudaStream_t st) {
+    k_bluestein_tables<<<(m + 127) / 128, 128, 0, st>>>(chirp_dev, bhat_dev, n, m);
+}
+
 size_t phd_fft_pass_table_entries(const FftPlan& pl) {
     size_t e = 0;
-    for (int f = 0; f < pl.nfac; f++) e += (size_t)(pl.fac[f] - 1) * (pl.n / pl.fac[f]);
+    const int len = pl.m > 0 ? pl.m : pl.n;
+    for (int f = 0; f < pl.nfac; f++) e += (size_t)(pl.fac[f] - 1) * (len / pl.fac[f]);
     return e;
 }
 
@@ -1064,9 +1161,10 @@ void phd_fft_fill_pass_tables(float2* dev, FftPlan& pl, cudaStream_t st) {
     int s = 1, off = 0;
     for (int f = 0; f < pl.nfac; f++) {
         const int r = pl.fac[f];
-        const int cnt = (r - 1) * (pl.n / r);
+        const int len = pl.m > 0 ? pl.m : pl.n;
+        const int cnt = (r - 1) * (len / r);
         pl.twp_off[f] = off;
-        if (cnt > 0) k_pass_twiddles<<<(cnt + 255) / 256, 256, 0, st>>>(dev + off, pl.n, r, s);
+        if (cnt > 0) k_pass_twiddles<<<(cnt + 255) / 256, 256, 0, st>>>(dev + off, len, r, s);
         off += cnt;
         s *= r;
     }
@@ -1170,7 +1268,7 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
         PHD_FFT_PLANS(PHD_X)
 #undef PHD_X
     }
-    size_t smem = (size_t)P.W * 4 * sizeof(float2);  // two row pairs, two buffers
+    size_t smem = (size_t)(row.m > 0 ? row.m : P.W) * 4 * sizeof(float2);  // two row pairs, two buffers (Bluestein: padded)
     const bool one_pair = smem > 200 * 1024;          // rows longer than 6400 pixels: one pair per CTA
     if (one_pair) smem /= 2;
     if (smem > 200 * 1024) return 1;
@@ -1189,7 +1287,7 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
 int phd_launch_fft_rows_gray(const float* gray32, const DevParams& P, const FftPlan& row, float2* specT, cudaStream_t st,
                              int* launches) {
     *launches += 1;
-    size_t smem = (size_t)P.W * 4 * sizeof(float2);
+    size_t smem = (size_t)(row.m > 0 ? row.m : P.W) * 4 * sizeof(float2);
     const bool one_pair = smem > 200 * 1024;
     if (one_pair) smem /= 2;
     if (smem > 200 * 1024) return 1;
@@ -1201,13 +1299,14 @@ int phd_launch_fft_rows_gray(const float* gray32, const DevParams& P, const FftP
     return 0;
 }
 
-size_t phd_fft_cols_smem(const DevParams& P, int* tile_cols) {
+size_t phd_fft_cols_smem(const DevParams& P, const FftPlan* col, int* tile_cols) {
     const size_t bins = (size_t)2 * P.nbins * sizeof(u32);
     const size_t budget = 110 * 1024;  // two CTAs per SM
+    const size_t len = (col && col->m > 0) ? (size_t)col->m : (size_t)P.Hp;  // Bluestein: the padded length
     int tc = 8;
-    while (tc > 1 && (size_t)tc * P.Hp * 2 * sizeof(float2) + bins > budget) tc >>= 1;
+    while (tc > 1 && (size_t)tc * len * 2 * sizeof(float2) + bins > budget) tc >>= 1;
     *tile_cols = tc;
-    return (size_t)tc * P.Hp * 2 * sizeof(float2) + bins;
+    return (size_t)tc * len * 2 * sizeof(float2) + bins;
 }
 
 int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, float2* specT, const u16* binmapT,
@@ -1222,7 +1321,7 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
         }
     }
     int tc;
-    const size_t smem = phd_fft_cols_smem(P, &tc);
+    const size_t smem = phd_fft_cols_smem(P, &col, &tc);
     if (smem > 200 * 1024) return 1;
     PHD_ALLOW_SMEM((k_cols_generic<false>), 200 * 1024);
     PHD_ALLOW_SMEM((k_cols_generic<true>), 200 * 1024);

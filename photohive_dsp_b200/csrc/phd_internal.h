@@ -100,9 +100,14 @@ struct SharpAcc {
 
 struct FftPlan {
     int n;
+    int m;      // 0: the radix plan below is that of length n.  > 0: Bluestein -- length n has a large prime factor, the
+                // transform is a circular convolution through length m >= 2n-1 (a product of small radices), and the
+                // radix plan and pass tables below are those of length m
     int nfac;
     int fac[PHD_MAX_FACTORS];
     int twp_off[PHD_MAX_FACTORS];  // start of pass f's table inside twp
+    const float2* chirp;  // Bluestein: n entries exp(-i pi k^2 / n)
+    const float2* bhat;   // Bluestein: m entries, the length-m transform of the conjugate chirp, divided by m
     const float2* tw;   // device, n entries exp(-2 pi i k / n)
     const float2* twp;  // device, per-pass tables: pass f (radix r, m = n/r butterflies) reads
                         // twp[twp_off[f] + (j-1)*m + b], j = 1..r-1 -- consecutive lanes, consecutive entries
@@ -173,6 +178,8 @@ size_t phd_cell_tables_size();
 size_t phd_pixels_smem(const DevParams& P);
 
 int phd_fft_plan_factors(int n, int* fac, int* nfac);  // 0 ok, nonzero unsupported
+int phd_fft_make_plan(int n, FftPlan* pl);             // radix plan of n, or a Bluestein plan (pl->m > 0); 0 ok
+void phd_fft_fill_bluestein(float2* chirp_dev, float2* bhat_dev, int n, int m, cudaStream_t st);
 void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st);
 size_t phd_fft_pass_table_entries(const FftPlan& pl);
 void phd_fft_fill_pass_tables(float2* dev, FftPlan& pl, cudaStream_t st);  // also sets pl.twp_off / pl.twp
@@ -191,7 +198,7 @@ void phd_launch_finalize(const DevParams& P, int nimg, const double* centres, co
                          const phd_flat_layout& lay, unsigned char* records_dev, cudaStream_t st, int* launches,
                          const F64Work* f64 = nullptr);
 
-size_t phd_fft_cols_smem(const DevParams& P, int* tile_cols);
+size_t phd_fft_cols_smem(const DevParams& P, const FftPlan* col, int* tile_cols);
 
 // general-input route (f64path.cu)
 void phd_launch_f64_front(const double* planes, const DevParams& P, F64Work& fw, Workspace& ws, cudaStream_t st, int* launches);

@@ -316,20 +316,30 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
     }
     ShapePlan s;
     s.W = W; s.H = H; s.nr = nr; s.na = na;
-    s.row.n = W; s.col.n = H;
-    if (phd_fft_plan_factors(W, s.row.fac, &s.row.nfac) || phd_fft_plan_factors(H, s.col.fac, &s.col.nfac))
+    if (phd_fft_make_plan(W, &s.row) || phd_fft_make_plan(H, &s.col))
         return fail(ctx, PHD_E_UNSUPPORTED, "image side has too many or too large prime factors: FFT length not supported by this build");
     const int Hp = (H + 3) / 4 * 4;
     const size_t nspec = (size_t)(W / 2 + 1) * Hp;
     const size_t pe_row = phd_fft_pass_table_entries(s.row), pe_col = phd_fft_pass_table_entries(s.col);
-    CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * (W + pe_row)));
-    CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * (H + pe_col)));
+    // one allocation per direction: n twiddles, the pass tables, and for a Bluestein plan the chirp (n) and its transform (m)
+    CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * (W + pe_row + (s.row.m > 0 ? W + s.row.m : 0))));
+    CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * (H + pe_col + (s.col.m > 0 ? H + s.col.m : 0))));
     CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
     CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
     phd_fill_twiddles(s.tw_row, W, ctx->stream);
     phd_fill_twiddles(s.tw_col, H, ctx->stream);
     phd_fft_fill_pass_tables(s.tw_row + W, s.row, ctx->stream);
     phd_fft_fill_pass_tables(s.tw_col + H, s.col, ctx->stream);
+    if (s.row.m > 0) {
+        float2* chirp = s.tw_row + W + pe_row;
+        phd_fft_fill_bluestein(chirp, chirp + W, W, s.row.m, ctx->stream);
+        s.row.chirp = chirp; s.row.bhat = chirp + W;
+    }
+    if (s.col.m > 0) {
+        float2* chirp = s.tw_col + H + pe_col;
+        phd_fft_fill_bluestein(chirp, chirp + H, H, s.col.m, ctx->stream);
+        s.col.chirp = chirp; s.col.bhat = chirp + H;
+    }
     phd_launch_bin_map(W, H, Hp, nr, na, s.binmap, s.bincount, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
@@ -541,7 +551,8 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
         for (int b = 0; b < 2; b++)
             if ((rc = ensure_bytes(ctx, &ctx->d_stage[b], &ctx->d_stage_bytes[b], dev_stride * pb)) != PHD_OK) return rc;
     int tc;
-    if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024)
+    if ((size_t)(shape->row.m > 0 ? shape->row.m : P.W) * 2 * sizeof(float2) > 200 * 1024 ||
+        phd_fft_cols_smem(P, &shape->col, &tc) > 200 * 1024)
         return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
 
     cudaStream_t st = ctx->stream;
@@ -687,8 +698,8 @@ int run_pipeline_f64(phd_context* ctx, const double* planes_dev, int W, int H, c
     if ((rc = get_tables(ctx, p, &tab)) != PHD_OK) return rc;
     if ((rc = ensure_workspace(ctx, P, 1, 1)) != PHD_OK) return rc;
     int tc;
-    if ((size_t)P.W * 2 * sizeof(float2) > 200 * 1024 || phd_fft_cols_smem(P, &tc) > 200 * 1024 ||
-        phd_f64_accumulate_smem(P) > 200 * 1024)
+    if ((size_t)(shape->row.m > 0 ? shape->row.m : P.W) * 2 * sizeof(float2) > 200 * 1024 ||
+        phd_fft_cols_smem(P, &shape->col, &tc) > 200 * 1024 || phd_f64_accumulate_smem(P) > 200 * 1024)
         return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
     P.cpp = P.nchunks;  // one span: the tie path of this route ranks pixels itself, nothing is folded from span sums
     P.nspans = 1;

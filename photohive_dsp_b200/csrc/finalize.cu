@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
     const ImageAcc a = iacc[img];
     const double np = (double)P.npx;
     const int N = pal_n[img];
+    // records carry padding bytes nothing below writes: clear the record here so that equal images give equal bytes
+    // (this used to be a separate memset per call)
+    for (size_t i = tid; i < lay.record_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(rec)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
 
     // --- partly accepted tie groups: fold the pixels k_palette_ties accepted into their parent's sums ---
     {
@@ -133,6 +137,13 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
         out_sharp[k] = r;
     }
     __syncthreads();
+    // per-angle sums of the first nr / denom radius bins (vectorize_blur_profile, src/blur_profile.c:340-350)
+    for (int i = tid; i < P.na; i += blockDim.x) {
+        double t = 0;
+        for (int j = 0; j < P.nr / P.denom; j++) t += bins[i * P.nr + j];
+        bins[P.nbins + i] = t;
+    }
+    __syncthreads();
 
     if (tid == 0) {
         for (int c = 0; c < 3 && f64_acc; c++) {
@@ -168,12 +179,7 @@ __global__ void __launch_bounds__(256) k_finalize(DevParams P, const double* __r
         double* tot = bins + P.nbins;
         double* sm = tot + na;
         double avg = 0;
-        for (int i = 0; i < na; i++) {
-            double t = 0;
-            for (int j = 0; j < rc; j++) t += bins[i * nr + j];
-            tot[i] = t;
-            avg += t;
-        }
+        for (int i = 0; i < na; i++) avg += tot[i];  // tot[] was summed by na threads above, each in the reference's order
         avg /= na;
         for (int i = 0; i < na; i++) {
             double r = 0;

@@ -269,10 +269,22 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
             }
         }
         plan_g[(size_t)img * T + g] = gp;
-        // everything that joins a parent as a whole: fold its cells into the parent's sums
-        if (gp.mode == 1 && !from_hist) {
-            const GroupSums S = phd_reduce_group(cells, P, g, gh[ids[gp.slot]]);
-            SlotAcc* a = sacc + (size_t)img * T + gp.slot;
+        pend[g] = gp.mode;  // (pend[] and fill[] are dead: reused as the group's mode and parent slot for the fold below)
+        fill[g] = gp.slot;
+    }
+    __syncthreads();
+    // Everything that joins a parent as a whole: fold its cells into the parent's sums.  One thread per (class, hue bin)
+    // pair, not per group: the gray and the black group span every hue bin, and a single thread walking their 4 * hp cells
+    // with dependent global loads was most of this kernel's latency for a single image.
+    if (!from_hist) {
+        const int spvp = P.sp * P.vp;
+        for (int pair = tid; pair < P.ncls * P.hp; pair += blockDim.x) {
+            const int cls = pair / P.hp, j = pair - cls * P.hp;
+            const int g = cls < spvp ? j * spvp + cls : (cls == spvp ? T - (P.vp + 1) : T - 1);
+            if (pend[g] != 1) continue;
+            GroupSums S{0, 0, 0, 0, 0};
+            phd_reduce_pair(cells, P.NC, pair, j, P.Lh, 180.0 - gh[ids[fill[g]]], S);
+            SlotAcc* a = sacc + (size_t)img * T + fill[g];
             if (S.summax) atomicAdd(&a->summax, S.summax);
             if (S.n255) atomicAdd(&a->n255, S.n255);
             if (S.s_sum) atomicAdd(&a->s_sum, S.s_sum);
@@ -336,17 +348,46 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
                 gp->clast = clast;
                 if (clast >= 0) atomicOr(&cbits[clast >> 5], 1u << (clast & 31));
             }
-            if (from_hist) continue;  // the general-input route accumulates pixels, not cells
-            // its tie cells: the sums of the wholly accepted spans (zero when there is none)
-            u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
+            if (lane == 0) take[g] = sstar;  // (take[] is dead from here on: reused for the fold below)
+        }
+    }
+    __syncthreads();
+    // Tie cells of every partly accepted group: the sums of its wholly accepted spans (zero when there is none).  All
+    // threads share the (quantity, cell) items; a thread walks the spans of its item with eight loads in flight.
+    if (!from_hist) {
+        u64* ct = cells_tie_g + (size_t)img * PHD_CELL_Q * P.NC;
+        for (int e = 0; e < sh_nscan; e++) {
+            const int g = scan_list[e], sstar = take[g];
             int c0, nc;
             phd_group_cell_range(P, g, &c0, &nc);
-            for (int i = lane; i < PHD_CELL_Q * nc; i += 32) {
+            for (int i = tid; i < PHD_CELL_Q * nc; i += blockDim.x) {
                 const int q = i / nc, cell = c0 + (i % nc);
+                const size_t s0 = (size_t)img * P.nspans;
                 u64 v = 0;
-                for (int sp = 0; sp < sstar; sp++) {
-                    const size_t sidx = (size_t)img * P.nspans + sp;
-                    v += q < 3 ? (u64)span32[(sidx * 3 + q) * P.NC + cell] : span64[(sidx * 2 + (q - 3)) * P.NC + cell];
+                if (q < 3) {
+                    const u32* b = span32 + (s0 * 3 + q) * P.NC + cell;
+                    const size_t st = (size_t)3 * P.NC;
+                    int sp = 0;
+                    for (; sp + 8 <= sstar; sp += 8) {
+                        u32 t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) t[u] = b[(size_t)(sp + u) * st];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v += t[u];
+                    }
+                    for (; sp < sstar; sp++) v += b[(size_t)sp * st];
+                } else {
+                    const u64* b = span64 + (s0 * 2 + (q - 3)) * P.NC + cell;
+                    const size_t st = (size_t)2 * P.NC;
+                    int sp = 0;
+                    for (; sp + 8 <= sstar; sp += 8) {
+                        u64 t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) t[u] = b[(size_t)(sp + u) * st];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v += t[u];
+                    }
+                    for (; sp < sstar; sp++) v += b[(size_t)sp * st];
                 }
                 ct[(size_t)q * P.NC + cell] = v;
             }

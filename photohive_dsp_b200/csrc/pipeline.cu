@@ -630,8 +630,6 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
                                           cudaMemcpyHostToDevice, st));
         }
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
-        // records carry padding bytes no kernel writes: clear them so equal images give equal bytes
-        CUDA_TRY(ctx, cudaMemsetAsync(records_dev + (size_t)first * lay.record_bytes, 0, lay.record_bytes * (size_t)n, st));
         phd_fe_plan(P, n);
         mark(&e0);
         // PHD_FUSED=1: front end and row FFT as one launch of role-switching persistent CTAs (fft.cu: k_front_rows) where
@@ -722,7 +720,6 @@ int run_pipeline_f64(phd_context* ctx, const double* planes_dev, int W, int H, c
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ws.boxes, boxes_host, sizeof(int) * 4 * (size_t)max_boxes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->ws_zero, 0, ctx->ws_zero_bytes, st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->f64_zero, 0, zbytes, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(records_dev, 0, lay.record_bytes, st));
     phd_launch_f64_front(planes_dev, P, fw, ctx->ws, st, &launches);
     phd_launch_palette_select(P, 1, tab->centres, tab->sv_f, ctx->ws, st, &launches, true);
     phd_launch_f64_accumulate(planes_dev, P, tab->centres, fw, ctx->ws, st, &launches);

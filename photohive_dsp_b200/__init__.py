@@ -1,13 +1,14 @@
 """photohive_dsp_b200 -- B200-native implementation of PhotoHive_DSP's get_report() hot path.
 
 Drop-in surface (same names as the reference package): ``get_report``, ``set_bounding_boxes``, ``Report``.
-Additive: ``get_reports`` / ``Context`` for batches of 8-bit images on one GPU, ``shard`` for N GPUs.
+Additive: ``get_reports`` / ``Context`` for batches of 8-bit images on one GPU, ``MultiContext`` for one host batch over
+several GPUs of one process, ``shard`` for one process per GPU.
 
 Attributes resolve lazily so that ``python -m photohive_dsp_b200.build`` can (re)build the shared library
 before anything tries to load it.
 """
 _CORE = {"Report", "get_report", "get_reports", "set_bounding_boxes"}
-_BATCH = {"BatchReports", "Context", "PhotoHiveError", "make_params"}
+_BATCH = {"BatchReports", "Context", "MultiContext", "PhotoHiveError", "make_params"}
 __all__ = sorted(_CORE | _BATCH)
 
 

@@ -1000,6 +1000,162 @@ __global__ void k_bin_map(int W, int H, int Hp, int nr, int na, u16* __restrict_
     atomicAdd(&counts[bin], 1);
 }
 
+// ------------------------------------------------------------------------------------------
+// Transforms that do not fit shared memory (image sides beyond 12,800 / ~11,000 pixels; src/utilities.c:11-13 admits
+// 120 MP at aspect <= 5, i.e. sides up to 24,494): four-step through HBM.  L = n1 * n2,
+//   X[k1 + n1 k2] = sum_j2 W_L^(j2 k1) [ sum_j1 x[j1 n2 + j2] W_n1^(j1 k1) ] W_n2^(j2 k2):
+// stage A transforms the n2 strided sub-sequences of length n1 (a tile of them per CTA, coalesced along j2), applies the
+// twiddle and stores [k1][j2]; stage B transforms the n1 contiguous sub-sequences of length n2 and stores X in natural
+// order.  Both run the runtime-radix passes on their tiles in shared memory.  A length without a usable factorisation
+// goes through Bluestein around the same two stages.  A rare path (panoramas): correctness first, several HBM passes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_long_stage_a(const float2* __restrict__ src, float2* __restrict__ dst, size_t stride,
+                                                      FftPlan p1, int n1, int n2, int L, const float2* __restrict__ twL,
+                                                      int TB) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);
+    float2* bufB = bufA + (size_t)TB * n1;
+    const size_t seq = blockIdx.y;
+    const int j20 = blockIdx.x * TB, nt = min(TB, n2 - j20);
+    const float2* s = src + seq * stride;
+    for (int idx = threadIdx.x; idx < nt * n1; idx += blockDim.x) {
+        const int j1 = idx / nt, t = idx - j1 * nt;
+        bufA[t * n1 + j1] = s[(size_t)j1 * n2 + j20 + t];
+    }
+    __syncthreads();
+    const float2* r = fft_run_rt(p1, bufA, bufB, nt, n1);
+    float2* d = dst + seq * stride;
+    for (int idx = threadIdx.x; idx < nt * n1; idx += blockDim.x) {
+        const int k1 = idx / nt, t = idx - k1 * nt, j2 = j20 + t;
+        const float2 w = __ldg(&twL[(int)(((long long)j2 * k1) % L)]);
+        d[(size_t)k1 * n2 + j2] = cmulf<false>(r[t * n1 + k1], w);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_long_stage_b(const float2* __restrict__ src, float2* __restrict__ dst, size_t stride,
+                                                      FftPlan p2, int n1, int n2, int TB) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);
+    float2* bufB = bufA + (size_t)TB * n2;
+    const size_t seq = blockIdx.y;
+    const int k10 = blockIdx.x * TB, nt = min(TB, n1 - k10);
+    const float2* s = src + seq * stride + (size_t)k10 * n2;
+    for (int idx = threadIdx.x; idx < nt * n2; idx += blockDim.x) bufA[idx] = s[idx];
+    __syncthreads();
+    const float2* r = fft_run_rt(p2, bufA, bufB, nt, n2);
+    float2* d = dst + seq * stride;
+    for (int idx = threadIdx.x; idx < nt * n2; idx += blockDim.x) {
+        const int k2 = idx / nt, t = idx - k2 * nt;
+        d[(size_t)(k10 + t) + (size_t)n1 * k2] = r[t * n2 + k2];
+    }
+}
+
+// Bluestein around the long transform (see fft_run_blue): x w, zero padded | conj(. * bhat) | conj(.) * w
+__global__ void k_long_chirp_in(float2* __restrict__ data, size_t stride, int n, int L, const float2* __restrict__ chirp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    float2* p = data + (size_t)blockIdx.y * stride + k;
+    *p = k < n ? cmulf<false>(*p, __ldg(&chirp[k])) : make_float2(0.f, 0.f);
+}
+__global__ void k_long_mul_bhat(float2* __restrict__ data, size_t stride, int L, const float2* __restrict__ bhat) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    float2* p = data + (size_t)blockIdx.y * stride + k;
+    const float2 v = cmulf<false>(*p, __ldg(&bhat[k]));
+    *p = make_float2(v.x, -v.y);
+}
+__global__ void k_long_chirp_out(float2* __restrict__ data, size_t stride, int n, const float2* __restrict__ chirp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float2* p = data + (size_t)blockIdx.y * stride + k;
+    const float2 v = *p;
+    *p = cmulf<false>(make_float2(v.x, -v.y), __ldg(&chirp[k]));
+}
+// tables of a long plan: W_L^k, and for Bluestein the chirp and the circular conjugate chirp (to be transformed)
+__global__ void k_long_tables(float2* __restrict__ twL, float2* __restrict__ chirp, float2* __restrict__ bpad, int n, int L,
+                              int blue) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    double sn, cs;
+    sincospi(2.0 * (double)k / (double)L, &sn, &cs);
+    twL[k] = make_float2((float)cs, (float)(-sn));
+    if (!blue) return;
+    // bpad[j] = exp(+i pi j^2 / n) for |j| < n laid out circularly, 0 elsewhere
+    const int j = k < n ? k : (k > L - n ? L - k : -1);
+    if (j >= 0) {
+        sincospi((double)(((long long)j * j) % (2LL * n)) / (double)n, &sn, &cs);
+        bpad[k] = make_float2((float)cs, (float)sn);
+        if (k < n) chirp[k] = make_float2((float)cs, (float)(-sn));
+    } else {
+        bpad[k] = make_float2(0.f, 0.f);
+    }
+}
+__global__ void k_long_scale(float2* __restrict__ data, int L, float f) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < L) data[k] = make_float2(data[k].x * f, data[k].y * f);
+}
+
+// rows of one image as packed pairs: data[pair][x] = (gray(row 2 pair, x), gray(row 2 pair + 1, x)) numerators
+__global__ void __launch_bounds__(256) k_long_gray(const uint8_t* __restrict__ rgb, const float* __restrict__ gray32, DevParams P,
+                                                   float2* __restrict__ data, size_t stride) {
+    const int pair = blockIdx.y;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < P.W; x += gridDim.x * blockDim.x) {
+        float g[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int row = 2 * pair + h;
+            if (row >= P.H) g[h] = 0.f;
+            else if (gray32) g[h] = __ldg(gray32 + (size_t)row * P.W + x);
+            else {
+                const uint8_t* px = rgb + ((size_t)row * P.W + x) * 3;
+                g[h] = (float)(299 * (int)__ldg(px) + 587 * (int)__ldg(px + 1) + 114 * (int)__ldg(px + 2) - PHD_GRAY_BIAS);
+            }
+        }
+        data[(size_t)pair * stride + x] = make_float2(g[0], g[1]);
+    }
+}
+// split the pair spectra into the two rows' half spectra and write them transposed (see k_rows_generic)
+__global__ void __launch_bounds__(256) k_long_rows_out(const float2* __restrict__ data, size_t stride, DevParams P,
+                                                       float2* __restrict__ specT) {
+    const int pair = blockIdx.y;
+    const float2* z = data + (size_t)pair * stride;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.fw; k += gridDim.x * blockDim.x) {
+        const int kc = k == 0 ? 0 : P.W - k;
+        const float2 zk = z[k], zc = z[kc];
+        *reinterpret_cast<float4*>(specT + (size_t)k * P.Hp + 2 * pair) =
+            make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+    }
+}
+__global__ void __launch_bounds__(256) k_long_cols_in(const float2* __restrict__ specT, DevParams P, float2* __restrict__ data,
+                                                      size_t stride) {
+    const int x = blockIdx.y;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.H; k += gridDim.x * blockDim.x)
+        data[(size_t)x * stride + k] = specT[(size_t)x * P.Hp + k];
+}
+// one CTA per transformed column (in HBM): the same epilogue as the shared-memory column kernels
+template <bool WRITE_POWER>
+__global__ void __launch_bounds__(kColThreads) k_long_cols_epi(DevParams P, float2* __restrict__ data, size_t stride,
+                                                               const u16* __restrict__ binmapT,
+                                                               const ImageAcc* __restrict__ iacc, u64* __restrict__ binsum,
+                                                               u32* __restrict__ maxpow, float* __restrict__ power_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32* bin_lo = reinterpret_cast<u32*>(smem_raw);
+    u32* bin_hi = bin_lo + P.nbins;
+    __shared__ float sh_max[kColThreads / 32];
+    const int x = blockIdx.x;
+    float2* res = data + (size_t)x * stride;
+    if (WRITE_POWER) {
+        cols_write_power(P, 0, x, 1, res, 0, power_out);
+        return;
+    }
+    for (int b = threadIdx.x; b < 2 * P.nbins; b += blockDim.x) bin_lo[b] = 0;
+    if (x == 0 && threadIdx.x == 0) cols_fix_dc(P, iacc, 0, res);
+    __syncthreads();
+    const float mymax = cols_accumulate<8, 0>(P.H, 1, res, 0, binmapT + (size_t)x * P.Hp, 0, bin_lo, bin_hi, 0.f);
+    __syncthreads();
+    cols_flush(P, 0, mymax, bin_lo, bin_hi, sh_max, binsum, maxpow);
+}
+
 // ---- dispatch tables of the specialised shapes -------------------------------------------------
 template <int N, int R0, int R1, int R2, int R3, int PAIRS>
 void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
@@ -1338,4 +1494,135 @@ void phd_launch_bin_map(int W, int H, int Hp, int nr, int na, u16* map_dev, int*
     cudaMemsetAsync(counts_dev, 0, sizeof(int) * na * nr, st);
     cudaMemsetAsync(map_dev, 0, sizeof(u16) * (size_t)(W / 2 + 1) * Hp, st);
     k_bin_map<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, H, Hp, nr, na, map_dev, counts_dev);
+}
+
+// ------------------------------------------------------------------------------------------
+// Long transforms through HBM (kernels above): plan, run, and the row / column stages built on them.
+// ------------------------------------------------------------------------------------------
+namespace {
+bool long_smooth(int x) {  // every prime factor has a register butterfly or a cheap O(p^2) pass
+    for (int q = 2; q <= 40 && x > 1; q++)
+        while (x % q == 0) x /= q;
+    return x == 1;
+}
+bool long_split(int L, int* n1, int* n2) {
+    int r = (int)sqrt((double)L);
+    for (int d = r; d >= 2; d--) {
+        if (L % d) continue;
+        const int e = L / d;
+        if (e > 4096) break;
+        if (long_smooth(d) && long_smooth(e)) { *n1 = d; *n2 = e; return true; }
+    }
+    return false;
+}
+int long_tile(int len) {  // sub-sequences per CTA: two buffers of tile * len complex values within 96 KB
+    int tb = 6144 / len;
+    return tb < 1 ? 1 : (tb > 16 ? 16 : tb);
+}
+cudaError_t long_fft_raw(const PhdLongFft& lf, float2* data, float2* tmp, int nseq, size_t stride, cudaStream_t st,
+                         int* launches) {
+    const int ta = long_tile(lf.n1), tb = long_tile(lf.n2);
+    PHD_ALLOW_SMEM((k_long_stage_a), 100 * 1024);
+    PHD_ALLOW_SMEM((k_long_stage_b), 100 * 1024);
+    k_long_stage_a<<<dim3((lf.n2 + ta - 1) / ta, nseq), 256, (size_t)2 * ta * lf.n1 * sizeof(float2), st>>>(
+        data, tmp, stride, lf.p1, lf.n1, lf.n2, lf.L, lf.twL, ta);
+    k_long_stage_b<<<dim3((lf.n1 + tb - 1) / tb, nseq), 256, (size_t)2 * tb * lf.n2 * sizeof(float2), st>>>(
+        tmp, data, stride, lf.p2, lf.n1, lf.n2, tb);
+    *launches += 2;
+    return cudaGetLastError();
+}
+// transform of logical length lf.n of nseq sequences at `stride` (>= lf.L) complex values; result in data[.][0 .. n)
+cudaError_t long_fft_run(const PhdLongFft& lf, float2* data, float2* tmp, int nseq, size_t stride, cudaStream_t st,
+                         int* launches) {
+    if (!lf.blue) return long_fft_raw(lf, data, tmp, nseq, stride, st, launches);
+    const dim3 gl((lf.L + 255) / 256, nseq), gn((lf.n + 255) / 256, nseq);
+    k_long_chirp_in<<<gl, 256, 0, st>>>(data, stride, lf.n, lf.L, lf.chirp);
+    cudaError_t e = long_fft_raw(lf, data, tmp, nseq, stride, st, launches);
+    if (e != cudaSuccess) return e;
+    k_long_mul_bhat<<<gl, 256, 0, st>>>(data, stride, lf.L, lf.bhat);
+    e = long_fft_raw(lf, data, tmp, nseq, stride, st, launches);
+    if (e != cudaSuccess) return e;
+    k_long_chirp_out<<<gn, 256, 0, st>>>(data, stride, lf.n, lf.chirp);
+    *launches += 3;
+    return cudaGetLastError();
+}
+size_t sub_plan_entries(const FftPlan& pl) { return (size_t)pl.n + phd_fft_pass_table_entries(pl); }
+}  // namespace
+
+int phd_long_fft_create(int n, PhdLongFft* lf, cudaStream_t st) {
+    memset(lf, 0, sizeof(*lf));
+    lf->n = n;
+    lf->L = n;
+    if (!long_split(n, &lf->n1, &lf->n2)) {
+        lf->blue = 1;
+        long long best = 0;
+        for (long long a = 1; a < (1LL << 24); a *= 2)
+            for (long long b = a; b < (1LL << 24); b *= 3)
+                for (long long c = b; c < (1LL << 24); c *= 5)
+                    if (c >= 2LL * n - 1 && (best == 0 || c < best)) best = c;
+        lf->L = (int)best;
+        if (!long_split(lf->L, &lf->n1, &lf->n2)) return 1;
+    }
+    lf->p1.n = lf->n1;
+    lf->p2.n = lf->n2;
+    if (phd_fft_plan_factors(lf->n1, lf->p1.fac, &lf->p1.nfac) || phd_fft_plan_factors(lf->n2, lf->p2.fac, &lf->p2.nfac)) return 1;
+    const size_t e1 = sub_plan_entries(lf->p1), e2 = sub_plan_entries(lf->p2);
+    const size_t total = e1 + e2 + (size_t)lf->L + (lf->blue ? (size_t)n + lf->L : 0);
+    if (cudaMalloc(&lf->mem, sizeof(float2) * total) != cudaSuccess) return 2;
+    float2* t1 = lf->mem;
+    float2* t2 = t1 + e1;
+    float2* twL = t2 + e2;
+    float2* chirp = twL + lf->L;
+    float2* bhat = chirp + n;
+    phd_fill_twiddles(t1, lf->n1, st);
+    phd_fft_fill_pass_tables(t1 + lf->n1, lf->p1, st);
+    lf->p1.tw = t1;
+    phd_fill_twiddles(t2, lf->n2, st);
+    phd_fft_fill_pass_tables(t2 + lf->n2, lf->p2, st);
+    lf->p2.tw = t2;
+    lf->twL = twL;
+    float2* tmp = nullptr;
+    if (lf->blue && cudaMalloc(&tmp, sizeof(float2) * lf->L) != cudaSuccess) return 2;
+    k_long_tables<<<(lf->L + 255) / 256, 256, 0, st>>>(twL, lf->blue ? chirp : nullptr, lf->blue ? bhat : nullptr, n, lf->L, lf->blue);
+    if (lf->blue) {
+        // bhat = (1/L) * DFT_L of the circular conjugate chirp, by the long transform itself
+        lf->chirp = chirp;
+        lf->bhat = bhat;
+        int launches = 0;
+        const cudaError_t e = long_fft_raw(*lf, bhat, tmp, 1, (size_t)lf->L, st, &launches);
+        k_long_scale<<<(lf->L + 255) / 256, 256, 0, st>>>(bhat, lf->L, 1.0f / (float)lf->L);
+        cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return 2;
+    }
+    return cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+void phd_long_fft_destroy(PhdLongFft* lf) {
+    if (lf && lf->mem) cudaFree(lf->mem);
+    if (lf) memset(lf, 0, sizeof(*lf));
+}
+
+int phd_launch_long_rows(const uint8_t* rgb, const float* gray32, const DevParams& P, const PhdLongFft& lf, float2* buf0,
+                         float2* buf1, float2* specT, cudaStream_t st, int* launches) {
+    const int npairs = P.Hp / 2;
+    const size_t stride = (size_t)lf.L;
+    k_long_gray<<<dim3(32, npairs), 256, 0, st>>>(rgb, gray32, P, buf0, stride);
+    if (long_fft_run(lf, buf0, buf1, npairs, stride, st, launches) != cudaSuccess) return 1;
+    k_long_rows_out<<<dim3(16, npairs), 256, 0, st>>>(buf0, stride, P, specT);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int phd_launch_long_cols(const DevParams& P, const PhdLongFft& lf, const float2* specT, float2* buf0, float2* buf1,
+                         const u16* binmapT, Workspace& ws, float* power_out, cudaStream_t st, int* launches) {
+    const size_t stride = (size_t)lf.L;
+    k_long_cols_in<<<dim3(16, P.fw), 256, 0, st>>>(specT, P, buf0, stride);
+    if (long_fft_run(lf, buf0, buf1, P.fw, stride, st, launches) != cudaSuccess) return 1;
+    const size_t smem = (size_t)2 * P.nbins * sizeof(u32);
+    PHD_ALLOW_SMEM((k_long_cols_epi<false>), 100 * 1024);
+    if (power_out) k_long_cols_epi<true><<<P.fw, kColThreads, 0, st>>>(P, buf0, stride, binmapT, ws.iacc, ws.binsum, ws.maxpow, power_out);
+    else k_long_cols_epi<false><<<P.fw, kColThreads, smem, st>>>(P, buf0, stride, binmapT, ws.iacc, ws.binsum, ws.maxpow, nullptr);
+    *launches += 2;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -113,6 +113,29 @@ struct FftPlan {
                         // twp[twp_off[f] + (j-1)*m + b], j = 1..r-1 -- consecutive lanes, consecutive entries
 };
 
+// A transform too long for shared memory (image sides beyond 12,800 / ~11,000 pixels; the reference admits 24,494):
+// four-step through HBM, length L = n1 * n2, or Bluestein through such an L when n has no usable factorisation (fft.cu).
+struct PhdLongFft {
+    int n;        // logical length
+    int L;        // transformed length: n, or the Bluestein length >= 2n-1
+    int n1, n2;   // L = n1 * n2
+    int blue;     // 1: Bluestein
+    FftPlan p1, p2;        // runtime-radix plans of n1 and n2
+    float2* mem;           // one allocation holding every table below
+    const float2* twL;     // L entries exp(-2 pi i k / L)
+    const float2* chirp;   // n entries (Bluestein)
+    const float2* bhat;    // L entries (Bluestein)
+};
+int phd_long_fft_create(int n, PhdLongFft* lf, cudaStream_t st);  // 0 ok
+void phd_long_fft_destroy(PhdLongFft* lf);
+// rows of ONE image (packed bytes, or the float gray plane of the general-input route) -> transposed half spectrum
+int phd_launch_long_rows(const uint8_t* rgb, const float* gray32, const DevParams& P, const PhdLongFft& lf, float2* buf0,
+                         float2* buf1, float2* specT, cudaStream_t st, int* launches);
+// columns of ONE image + blur-profile epilogue (ws accumulators of that image), or the power spectrum (test hook)
+struct Workspace;
+int phd_launch_long_cols(const DevParams& P, const PhdLongFft& lf, const float2* specT, float2* buf0, float2* buf1,
+                         const u16* binmapT, Workspace& ws, float* power_out, cudaStream_t st, int* launches);
+
 // Device workspace for one sub-batch.
 struct Workspace {
     int capacity;  // images

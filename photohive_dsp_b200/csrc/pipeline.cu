@@ -25,6 +25,9 @@ struct ShapePlan {
     float2* tw_col = nullptr;
     u16* binmap = nullptr;
     int* bincount = nullptr;
+    // sides too long for the shared-memory kernels (fft.cu: four-step transforms through HBM)
+    bool long_row = false, long_col = false;
+    PhdLongFft lrow{}, lcol{};
 };
 
 struct ParamTables {
@@ -72,6 +75,8 @@ struct phd_context {
     size_t f64_zero_bytes = 0;
     unsigned char* f64_gray = nullptr;
     size_t f64_gray_bytes = 0;
+    unsigned char* long_buf[2] = {nullptr, nullptr};  // work buffers of the long (HBM) transforms, one image
+    size_t long_buf_bytes[2] = {0, 0};
     // uploader threads of the drop-in call: each owns a stream, two pinned slices and their "slice free again" events
     static constexpr int kUpThreads = 8;
     static constexpr size_t kUpSlice = 2u << 20;
@@ -312,24 +317,38 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         ShapePlan& old = ctx->shapes.front();
         cudaFree(old.tw_row); cudaFree(old.tw_col); cudaFree(old.binmap); cudaFree(old.bincount);
+        phd_long_fft_destroy(&old.lrow); phd_long_fft_destroy(&old.lcol);
         ctx->shapes.erase(ctx->shapes.begin());
     }
     ShapePlan s;
     s.W = W; s.H = H; s.nr = nr; s.na = na;
-    if (phd_fft_make_plan(W, &s.row) || phd_fft_make_plan(H, &s.col))
+    // sides beyond what two shared-memory buffers hold (rows: 12,800 pixels; columns: ~11,000 next to the blur bins) are
+    // transformed through HBM; the reference admits sides up to 24,494 (src/utilities.c:11-13)
+    s.long_row = (size_t)W * 2 * sizeof(float2) > 200 * 1024;
+    s.long_col = (size_t)((H + 3) / 4 * 4) * 2 * sizeof(float2) + (size_t)2 * nr * na * sizeof(u32) > 200 * 1024;
+    memset(&s.row, 0, sizeof(s.row));
+    memset(&s.col, 0, sizeof(s.col));
+    s.row.n = W; s.col.n = H;
+    if ((!s.long_row && phd_fft_make_plan(W, &s.row)) || (!s.long_col && phd_fft_make_plan(H, &s.col)))
         return fail(ctx, PHD_E_UNSUPPORTED, "image side has too many or too large prime factors: FFT length not supported by this build");
+    if ((s.long_row && phd_long_fft_create(W, &s.lrow, ctx->stream)) || (s.long_col && phd_long_fft_create(H, &s.lcol, ctx->stream)))
+        return fail(ctx, PHD_E_UNSUPPORTED, "cannot plan the long (HBM) transform of this image side");
     const int Hp = (H + 3) / 4 * 4;
     const size_t nspec = (size_t)(W / 2 + 1) * Hp;
-    const size_t pe_row = phd_fft_pass_table_entries(s.row), pe_col = phd_fft_pass_table_entries(s.col);
+    const size_t pe_row = s.long_row ? 0 : phd_fft_pass_table_entries(s.row), pe_col = s.long_col ? 0 : phd_fft_pass_table_entries(s.col);
     // one allocation per direction: n twiddles, the pass tables, and for a Bluestein plan the chirp (n) and its transform (m)
     CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * (W + pe_row + (s.row.m > 0 ? W + s.row.m : 0))));
     CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * (H + pe_col + (s.col.m > 0 ? H + s.col.m : 0))));
     CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
     CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
-    phd_fill_twiddles(s.tw_row, W, ctx->stream);
-    phd_fill_twiddles(s.tw_col, H, ctx->stream);
-    phd_fft_fill_pass_tables(s.tw_row + W, s.row, ctx->stream);
-    phd_fft_fill_pass_tables(s.tw_col + H, s.col, ctx->stream);
+    if (!s.long_row) {
+        phd_fill_twiddles(s.tw_row, W, ctx->stream);
+        phd_fft_fill_pass_tables(s.tw_row + W, s.row, ctx->stream);
+    }
+    if (!s.long_col) {
+        phd_fill_twiddles(s.tw_col, H, ctx->stream);
+        phd_fft_fill_pass_tables(s.tw_col + H, s.col, ctx->stream);
+    }
     if (s.row.m > 0) {
         float2* chirp = s.tw_row + W + pe_row;
         phd_fft_fill_bluestein(chirp, chirp + W, W, s.row.m, ctx->stream);
@@ -494,6 +513,51 @@ bool is_pageable_host_pointer(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// Row and column stage of `nimg` images: the shared-memory kernels, or image by image through HBM for long sides.
+int long_buffers(phd_context* ctx, const ShapePlan& shape, const DevParams& P) {
+    size_t need = 0;
+    if (shape.long_row) need = std::max(need, (size_t)(P.Hp / 2) * shape.lrow.L * sizeof(float2));
+    if (shape.long_col) need = std::max(need, (size_t)P.fw * shape.lcol.L * sizeof(float2));
+    for (int b = 0; b < 2 && need; b++) {
+        const int rc = ensure_bytes(ctx, &ctx->long_buf[b], &ctx->long_buf_bytes[b], need);
+        if (rc != PHD_OK) return rc;
+    }
+    return PHD_OK;
+}
+
+int launch_rows_any(phd_context* ctx, const ShapePlan& shape, const uint8_t* rgb, size_t image_stride, const float* gray32,
+                    const DevParams& P, int nimg, float2* spec, cudaStream_t st, int* launches) {
+    if (!shape.long_row) {
+        if (gray32) return phd_launch_fft_rows_gray(gray32, P, shape.row, spec, st, launches);
+        return phd_launch_fft_rows(rgb, P, nimg, shape.row, spec, st, launches);
+    }
+    int rc = long_buffers(ctx, shape, P);
+    if (rc != PHD_OK) return rc;
+    for (int i = 0; i < nimg; i++)
+        if (phd_launch_long_rows(rgb ? rgb + (size_t)i * image_stride : nullptr, gray32, P, shape.lrow,
+                                 reinterpret_cast<float2*>(ctx->long_buf[0]), reinterpret_cast<float2*>(ctx->long_buf[1]),
+                                 spec + (size_t)i * P.fw * P.Hp, st, launches))
+            return 1;
+    return 0;
+}
+
+int launch_cols_any(phd_context* ctx, const ShapePlan& shape, const DevParams& P, int nimg, float2* spec, Workspace& ws,
+                    float* power_out, cudaStream_t st, int* launches) {
+    if (!shape.long_col) return phd_launch_fft_cols_blur(P, nimg, shape.col, spec, shape.binmap, ws, power_out, st, launches);
+    int rc = long_buffers(ctx, shape, P);
+    if (rc != PHD_OK) return rc;
+    for (int i = 0; i < nimg; i++) {
+        Workspace one = ws;  // accumulators of image i
+        one.iacc += i;
+        one.binsum += (size_t)i * P.nbins;
+        one.maxpow += i;
+        if (phd_launch_long_cols(P, shape.lcol, spec + (size_t)i * P.fw * P.Hp, reinterpret_cast<float2*>(ctx->long_buf[0]),
+                                 reinterpret_cast<float2*>(ctx->long_buf[1]), shape.binmap, one, power_out, st, launches))
+            return 1;
+    }
+    return 0;
+}
+
 // Images per FFT sub-batch (the row-transformed spectra of one sub-batch live in `spec`).  Measured on B200
 // (profiles/): bigger launches win over keeping the spectra L2 resident (48.4 k images/s at 48 images per launch,
 // 50.5 k at 512 vs 45.9 k at 11), so the sub-batch is the whole palette batch, capped at 8 GB of spectra.
@@ -550,11 +614,6 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
     if (!input_on_device)
         for (int b = 0; b < 2; b++)
             if ((rc = ensure_bytes(ctx, &ctx->d_stage[b], &ctx->d_stage_bytes[b], dev_stride * pb)) != PHD_OK) return rc;
-    int tc;
-    if ((size_t)(shape->row.m > 0 ? shape->row.m : P.W) * 2 * sizeof(float2) > 200 * 1024 ||
-        phd_fft_cols_smem(P, &shape->col, &tc) > 200 * 1024)
-        return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
-
     cudaStream_t st = ctx->stream;
     ctx->spans.clear();
     ctx->events_used = 0;
@@ -654,12 +713,12 @@ int run_pipeline(phd_context* ctx, const uint8_t* rgb_host_or_dev, bool input_on
             sub.binsum += (size_t)f0 * P.nbins;
             sub.maxpow += f0;
             if (!fused) {
-                if (phd_launch_fft_rows(d_in + (size_t)f0 * dev_stride, P, nf, shape->row, ctx->ws.spec, st, &launches))
-                    return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
+                if (launch_rows_any(ctx, *shape, d_in + (size_t)f0 * dev_stride, dev_stride, nullptr, P, nf, ctx->ws.spec, st, &launches))
+                    return fail(ctx, PHD_E_UNSUPPORTED, "row FFT of this image width cannot be served");
                 mark(&e1); span(ST_ROWS, e0, e1); e0 = e1;
             }
-            if (phd_launch_fft_cols_blur(P, nf, shape->col, ctx->ws.spec, shape->binmap, sub, nullptr, st, &launches))
-                return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
+            if (launch_cols_any(ctx, *shape, P, nf, ctx->ws.spec, sub, nullptr, st, &launches))
+                return fail(ctx, PHD_E_UNSUPPORTED, "column FFT of this image height cannot be served");
             mark(&e1); span(ST_COLS, e0, e1); e0 = e1;
         }
         phd_launch_sharpness(d_in, P, n, max_w, max_h, ctx->ws, st, &launches);
@@ -695,10 +754,8 @@ int run_pipeline_f64(phd_context* ctx, const double* planes_dev, int W, int H, c
     if ((rc = get_shape(ctx, W, H, P.nr, P.na, &shape)) != PHD_OK) return rc;
     if ((rc = get_tables(ctx, p, &tab)) != PHD_OK) return rc;
     if ((rc = ensure_workspace(ctx, P, 1, 1)) != PHD_OK) return rc;
-    int tc;
-    if ((size_t)(shape->row.m > 0 ? shape->row.m : P.W) * 2 * sizeof(float2) > 200 * 1024 ||
-        phd_fft_cols_smem(P, &shape->col, &tc) > 200 * 1024 || phd_f64_accumulate_smem(P) > 200 * 1024)
-        return fail(ctx, PHD_E_UNSUPPORTED, "image side too long for the shared-memory FFT of this build");
+    if (phd_f64_accumulate_smem(P) > 200 * 1024)
+        return fail(ctx, PHD_E_UNSUPPORTED, "palette grid too fine for the general-input route of this build");
     P.cpp = P.nchunks;  // one span: the tie path of this route ranks pixels itself, nothing is folded from span sums
     P.nspans = 1;
     const size_t nb1 = max_boxes > 0 ? max_boxes : 1;
@@ -723,10 +780,10 @@ int run_pipeline_f64(phd_context* ctx, const double* planes_dev, int W, int H, c
     phd_launch_f64_front(planes_dev, P, fw, ctx->ws, st, &launches);
     phd_launch_palette_select(P, 1, tab->centres, tab->sv_f, ctx->ws, st, &launches, true);
     phd_launch_f64_accumulate(planes_dev, P, tab->centres, fw, ctx->ws, st, &launches);
-    if (phd_launch_fft_rows_gray(fw.gray32, P, shape->row, ctx->ws.spec, st, &launches))
-        return fail(ctx, PHD_E_UNSUPPORTED, "row FFT does not fit shared memory");
-    if (phd_launch_fft_cols_blur(P, 1, shape->col, ctx->ws.spec, shape->binmap, ctx->ws, nullptr, st, &launches))
-        return fail(ctx, PHD_E_UNSUPPORTED, "column FFT does not fit shared memory");
+    if (launch_rows_any(ctx, *shape, nullptr, 0, fw.gray32, P, 1, ctx->ws.spec, st, &launches))
+        return fail(ctx, PHD_E_UNSUPPORTED, "row FFT of this image width cannot be served");
+    if (launch_cols_any(ctx, *shape, P, 1, ctx->ws.spec, ctx->ws, nullptr, st, &launches))
+        return fail(ctx, PHD_E_UNSUPPORTED, "column FFT of this image height cannot be served");
     phd_launch_finalize(P, 1, tab->centres, shape->bincount, ctx->ws, lay, records_dev, st, &launches, &fw);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->last_launches = launches;
@@ -826,7 +883,10 @@ void phd_context_destroy(phd_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& s : ctx->shapes) { cudaFree(s.tw_row); cudaFree(s.tw_col); cudaFree(s.binmap); cudaFree(s.bincount); }
+    for (auto& s : ctx->shapes) {
+        cudaFree(s.tw_row); cudaFree(s.tw_col); cudaFree(s.binmap); cudaFree(s.bincount);
+        phd_long_fft_destroy(&s.lrow); phd_long_fft_destroy(&s.lcol);
+    }
     for (auto& t : ctx->tables) { cudaFree(t.centres); cudaFree(t.sv_f); cudaFree(t.tabs); }
     for (auto& e : ctx->exc_tables) cudaFree(e.second);
     Workspace& w = ctx->ws;
@@ -837,6 +897,7 @@ void phd_context_destroy(phd_context* ctx) {
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_planes); cudaFree(ctx->d_u8); cudaFree(ctx->d_flag);
     cudaFree(ctx->f64_zero); cudaFree(ctx->f64_gray);
+    cudaFree(ctx->long_buf[0]); cudaFree(ctx->long_buf[1]);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     for (int t = 0; t < phd_context::kUpThreads; t++) {
         if (ctx->up_stream[t]) cudaStreamDestroy(ctx->up_stream[t]);
@@ -1118,8 +1179,8 @@ int phd_debug_power_spectrum(phd_context* ctx, const uint8_t* rgb, int width, in
     int launches = 0;
     cudaError_t e = cudaMemcpyAsync(ctx->d_rgb, rgb, tight, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        if (phd_launch_fft_rows(ctx->d_rgb, P, 1, s->row, ctx->ws.spec, ctx->stream, &launches) ||
-            phd_launch_fft_cols_blur(P, 1, s->col, ctx->ws.spec, s->binmap, ctx->ws, d_pow, ctx->stream, &launches)) {
+        if (launch_rows_any(ctx, *s, ctx->d_rgb, stride, nullptr, P, 1, ctx->ws.spec, ctx->stream, &launches) ||
+            launch_cols_any(ctx, *s, P, 1, ctx->ws.spec, ctx->ws, d_pow, ctx->stream, &launches)) {
             cudaFree(d_pow);
             return fail(ctx, PHD_E_UNSUPPORTED, "FFT does not fit shared memory");
         }

@@ -93,6 +93,8 @@ def test_report_matches_oracle(ctx, oracle, W, H, kind, kw):
     (1920, 1080, 2, FINE, 0),
     (4000, 6000, 1, dict(downsample_rate=2), 0),  # portrait 24 MP, downsampled HSV grid
     (7680, 4320, 1, {}, 0),       # 33 MP: two groups' saliencies exceed 2^31 without any help from the weights
+    (13000, 2600, 1, {}, 1),      # a side beyond the shared-memory row FFT: four-step transform through HBM
+    (2602, 13003, 0, {}, 0),      # a prime column length beyond the shared-memory column FFT (Bluestein through HBM)
 ])
 def test_full_report_at_baseline_sizes(ctx, oracle, W, H, kind, kw, nbox):
     """BASELINE configs 4 and 5 as FULL reports against the oracle (the stages whose indexing changes with
@@ -497,7 +499,10 @@ def test_general_double_planes_match_oracle(oracle, W, H, kw, nbox):
                                  (4032, 3024), (3024, 4032), (5472, 3648), (3648, 5472), (4000, 3000), (3000, 4000),
                                  (3264, 2448), (2448, 3264), (4608, 3456), (3456, 4608), (1600, 1200), (1200, 1600),
                                  (1280, 960), (960, 1280), (2160, 3840), (1080, 1920), (4000, 6000), (480, 600), (600, 480),
-                                 (2011, 1511), (1511, 2011), (4030, 3020), (1031, 523)])  # prime sides: the O(p^2) pass
+                                 (2011, 1511), (1511, 2011), (4030, 3020), (1031, 523),   # prime sides: Bluestein
+                                 # sides beyond the shared-memory kernels: four-step transforms through HBM (13000 =
+                                 # 104 x 125), and Bluestein around them for a prime side (13003)
+                                 (13000, 2600), (2600, 13000), (13003, 2602), (2602, 13003)])
 def test_power_spectrum_against_float64_fft(ctx, oracle, W, H, record_property):
     """Every compile-time FFT plan (and the runtime-radix / Bluestein shapes) against numpy's float64 rfft2 of the same
     exact gray numerators, element by element (bounds and what is reported: tests/parity.py, "FFT magnitudes")."""

@@ -42,6 +42,18 @@ constexpr int kColThreads = 512;
 constexpr bool kColsPacked = true;  // column butterflies on the FP32x2 pipe (see Cx)
 constexpr int kColsMinBlocks1080 = 1; // register hint of the 1080-point column kernel (see k_cols_t)
 
+// Experiment knobs (-D...): pass twiddles generated from ONE loaded base twiddle per butterfly (w, w^2 = w*w, w^3 = w^2*w,
+// w^4 = (w^2)^2, ...: a product tree of depth <= 5) instead of R-1 table loads.
+#ifndef PHD_ROWS_TWPOW
+#define PHD_ROWS_TWPOW 1
+#endif
+#ifndef PHD_COLS_TWPOW
+#define PHD_COLS_TWPOW 1
+#endif
+#ifndef PHD_ROWS_PK
+#define PHD_ROWS_PK 0   // row butterflies on the packed FP32x2 pipe
+#endif
+
 // Complex arithmetic, scalar (PK = false) or on the packed FP32x2 pipe of sm_100 (PK = true: PTX
 // add/sub/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2, one instruction for both components, scalars broadcast
 // as an operand modifier).  Packed halves the instruction count of the complex adds and scalings but not their
@@ -250,7 +262,13 @@ __device__ __forceinline__ void seq_sync() {
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / GT), "n"(GT) : "memory");
 }
 
-template <int N, int R, int S, bool PADIN, int GT, bool PK>
+// w^2 for a unit complex w
+__device__ __forceinline__ float2 csqr(float2 w) { return make_float2(fmaf(w.x, w.x, -w.y * w.y), 2.0f * w.x * w.y); }
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+template <int N, int R, int S, bool PADIN, int GT, bool PK, bool TWPOW = false>
 __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
                                        const float2* __restrict__ twp, int nfft, int fstride_in, int fstride_out) {
     constexpr int M = N / R;
@@ -280,6 +298,16 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
         if (S * R == N) {  // last pass: every twiddle is 1
 #pragma unroll
             for (int j = 0; j < R; j++) y[q + j * S] = x[j];
+        } else if (TWPOW) {
+            // one table entry per butterfly (the j = 1 row), its powers by squaring / multiplying
+            float2 w[R];
+            w[1] = __ldg(&twp[b]);
+            y[R * pps + q] = x[0];
+#pragma unroll
+            for (int j = 1; j < R; j++) {
+                if (j > 1) w[j] = (j % 2 == 0) ? csqr(w[j / 2]) : cmul2(w[j - 1], w[1]);
+                y[R * pps + q + j * S] = cmulf<PK>(x[j], w[j]);
+            }
         } else {
             y[R * pps + q] = x[0];
 #pragma unroll
@@ -293,14 +321,14 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
 // whole passes, so a sequence must never be written into another sequence's region of either buffer.
 // Returns the buffer holding the result (unpadded; stride fstride for b, fstride_a for a).  The barrier after the
 // LAST pass is left to the caller (it usually needs a CTA-wide one there anyway).
-template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT, bool PK>
+template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT, bool PK, bool TWPOW = false>
 __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ twp, int nfft,
                                              int fstride_a, int fstride) {
     static_assert(R0 * R1 * R2 * R3 == N, "radix plan does not multiply to N");
     using PL = PlanT<N, R0, R1, R2, R3>;
-    pass_t<N, R0, 1, PADIN, GT, PK>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
+    pass_t<N, R0, 1, PADIN, GT, PK, TWPOW>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
     seq_sync<GT>();
-    pass_t<N, R1, R0, false, GT, PK>(b, a, twp + PL::off1, nfft, fstride, fstride_a);
+    pass_t<N, R1, R0, false, GT, PK, TWPOW>(b, a, twp + PL::off1, nfft, fstride, fstride_a);
     seq_sync<GT>();
     pass_t<N, R2, R0 * R1, false, GT, PK>(a, b, twp + PL::off2, nfft, fstride_a, fstride);
     if (R3 == 1) return b;
@@ -542,7 +570,7 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
             if (PREFETCH && q + q_step < q_end) load_step(q + q_step);
         }
         __syncthreads();  // CTA wide: the previous step's output loop (all threads read every pair's result) is over
-        const float2* z = fft_run_t<N, R0, R1, R2, R3, true, GT, false>(bufA, bufB, twp, PAIRS, NP, N);
+        const float2* z = fft_run_t<N, R0, R1, R2, R3, true, GT, PHD_ROWS_PK != 0, PHD_ROWS_TWPOW != 0>(bufA, bufB, twp, PAIRS, NP, N);
         __syncthreads();  // every pair's spectrum is complete
         float2* out = specT + (size_t)img * fw * P.Hp + 2 * PAIRS * q;
         for (int k = threadIdx.x; k < fw; k += blockDim.x) {
@@ -901,7 +929,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_cols_t(DevParams P, const
         const int it = g - g_begin;
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
         mbar_wait(&bar, it & 1);
-        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT, kColsPacked>(bufA, bufB, tw, ncol, N, N);
+        float2* res = fft_run_t<N, R0, R1, R2, R3, false, GT, kColsPacked, PHD_COLS_TWPOW != 0>(bufA, bufB, tw, ncol, N, N);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (g + 1 < g_end) {

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) k_palette_ties(const uint8_t* __restrict_
     const int npairs = P.ncls * P.hp, spvp = P.sp * P.vp;
     const u32 n_items = *work_n;
     if (blockIdx.x >= n_items) return;
+    exc = phd_exc_biased(exc);
     phd_cell_tabs_to_smem(tb_raw, tabs_g);
     const unsigned char* svtab = tb_raw;
     const int qs = 20;  // tie cells are kept in Q20 like the global cells
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) k_group_sweep(DevParams P, const unsigned
     const int R = (c >> 16) & 255, G = (c >> 8) & 255, B = c & 255;
     if (FAST) {
         const CellCfg K = phd_cell_cfg(P, 20);
-        const PixOut o = phd_pixel(R, G, B, tb_raw, K, exc);
+        const PixOut o = phd_pixel(R, G, B, tb_raw, K, phd_exc_biased(exc));
         out[c] = (u16)phd_cell_group(o.cell, P);
     } else {
         const HsvD px = phd_hsv_exact(R, G, B, k255);
@@ -262,8 +263,9 @@ __global__ void __launch_bounds__(256) k_build_cell_tables(DevParams P, unsigned
     }
 }
 
-// Exceptional-colour codes (pixel_cells.cuh): for every colour whose hue is exactly k * Lh/2, what the reference's
-// doubles make of it.  code = full << 7 | (cell delta + 4), relative to the ordinary cell cls*4hp + 2k + 1.
+// Exceptional-colour table (pixel_cells.cuh): for every colour whose hue is exactly k * Lh/2, what the reference's
+// doubles make of it, stored at entry (tri(max) + min, k) as (cell delta relative to the ordinary cell cls*4hp + 2k + 1,
+// full).  Every exceptional colour has its own entry ((max, min, k) determine the colour); the others stay zero.
 __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* __restrict__ out, int* __restrict__ ok) {
     __shared__ double k255[256];
     phd_fill_k255(k255);
@@ -271,7 +273,6 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;  // R | G << 8 | B << 16
     const int R = c & 255, G = (c >> 8) & 255, B = (c >> 16) & 255;
     const int mx = max(R, max(G, B)), mn = min(R, min(G, B)), q = mx - mn;
-    int code = 0;
     if (q != 0) {
         const bool isR = (R == mx), isG = (G == mx);
         const int p = isR ? (G - B) : (isG ? (B - R) : (R - G));
@@ -303,10 +304,11 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
                 delta = below ? -2 : 0;  // (j, end of the lower half) | (j, upper half)
                 full = below ? 1 : 0;
             }
-            code = (full << 7) | (delta + 4);
+            unsigned char* ent = out + 2 * ((size_t)(((mx * mx + mx) >> 1) + mn) * (2 * P.hp) + k);
+            ent[0] = (unsigned char)(signed char)delta;
+            ent[1] = (unsigned char)full;
         }
     }
-    out[c] = (unsigned char)code;
 }
 
 }  // namespace
@@ -368,7 +370,12 @@ void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const
 void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev, unsigned char* exc_dev, int* ok_dev,
                                   cudaStream_t st) {
     k_build_cell_tables<<<1, 256, 0, st>>>(P, tables_dev, ok_dev);
-    if (exc_dev) k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
+    if (exc_dev) {
+        cudaMemsetAsync(exc_dev, 0, phd_exc_bytes(P.hp), st);
+        k_build_exc<<<(1 << 24) / 256, 256, 0, st>>>(P, exc_dev, ok_dev);
+    }
 }
+
+size_t phd_exc_table_bytes(int hp) { return phd_exc_bytes(hp); }
 
 size_t phd_cell_tables_size() { return 2 * phd_cell_tables_bytes(); }  // ordinary classes, then the table with twin classes

@@ -210,7 +210,7 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
     }
     {   // keep the table pointer in registers: the compiler would reload it from the constant bank per pixel
         unsigned long long e;
-        asm volatile("mov.u64 %0, %1;" : "=l"(e) : "l"(exc));
+        asm volatile("mov.u64 %0, %1;" : "=l"(e) : "l"(phd_exc_biased(exc)));
         exc = reinterpret_cast<const unsigned char*>(e);
     }
     const u32 cw_base0 = (u32)__cvta_generic_to_shared(chunkW);

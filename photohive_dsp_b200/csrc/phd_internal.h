@@ -195,6 +195,7 @@ void phd_launch_palette_ties(const uint8_t* rgb, const DevParams& P, int nimg, c
                              const unsigned char* exc, Workspace& ws, cudaStream_t st, int* launches);
 void phd_launch_group_sweep(const DevParams& P, const unsigned char* tabs, const unsigned char* exc, bool fast,
                             u16* out_dev, cudaStream_t st);
+size_t phd_exc_table_bytes(int hp);  // exceptional-colour table of h_partitions = hp (pixel_cells.cuh)
 void phd_launch_build_cell_tables(const DevParams& P, unsigned char* tables_dev, unsigned char* exc_dev, int* ok_dev,
                                   cudaStream_t st);
 size_t phd_cell_tables_size();

@@ -35,7 +35,7 @@ struct ParamTables {
     double* centres = nullptr;  // device [3*T]: group centre h, s, v
     float* sv_f = nullptr;      // device [T]: (float)(s*v) of the centre
     unsigned char* tabs = nullptr;  // device: class / reciprocal tables of pixel_cells.cuh
-    unsigned char* exc = nullptr;   // device: 2^24 exceptional-colour codes (pixel_cells.cuh); shared by every
+    unsigned char* exc = nullptr;   // device: exceptional-colour table (pixel_cells.cuh, phd_exc_bytes); shared by every
                                     // parameter set with the same h_partitions, owned by phd_context::exc_tables
 };
 
@@ -47,7 +47,7 @@ struct phd_context {
     std::mutex mu;
     std::vector<ShapePlan> shapes;
     std::vector<ParamTables> tables;
-    std::vector<std::pair<int, unsigned char*>> exc_tables;  // (h_partitions, 16 MB code table)
+    std::vector<std::pair<int, unsigned char*>> exc_tables;  // (h_partitions, exceptional-colour table: 2.4 MB at 18 bins)
     Workspace ws{};
     unsigned char* ws_zero = nullptr;  // one allocation holding every accumulator that must start at zero
     size_t ws_zero_bytes = 0;
@@ -285,7 +285,7 @@ int get_tables(phd_context* ctx, const phd_params& p, ParamTables** out) {
                 }
             }
         }
-        CUDA_TRY(ctx, cudaMalloc(&new_exc, (size_t)1 << 24));
+        CUDA_TRY(ctx, cudaMalloc(&new_exc, phd_exc_table_bytes(hp)));
         t.exc = new_exc;
     }
     CUDA_TRY(ctx, cudaMalloc(&ok_dev, sizeof(int)));

@@ -22,8 +22,14 @@
 // across a half-bin boundary.  rem == 0 ("exceptional", ~2-15 % of 8-bit pixels): the pixel is exactly on a
 // boundary and the reference's IEEE-double result decides (a) its hue bin, (b) on which side of a wrap seam it
 // falls.  Both are pure functions of the 24-bit colour and h_partitions; k_build_exc evaluates the reference's
-// double arithmetic (hsv_exact.cuh) once for all 2^24 colours into a 16 MB code table that the pixel loop reads
-// for exceptional pixels only.  tests/test_gpu_parity.py sweeps all 2^24 colours against the CPU oracle.
+// double arithmetic (hsv_exact.cuh) once for all 2^24 colours into a code table that the pixel loop reads for
+// exceptional pixels only.  An exceptional colour is identified by (max, min, half bin) -- the hue k * Lh/2 fixes sector
+// and p, hence the third channel -- so the table is exc[tri(max, min)][2 hp] of TWO bytes: (cell delta, signed; 1 if the
+// hue fraction counts as the END of its half bin): 2.4 MB at 18 hue bins instead of a byte per 24-bit colour (16 MB),
+// indexed by two numbers the loop has anyway (the class-table index and the half bin), and applied with two
+// multiply-adds -- the pixel loop is bound by the ALU pipe (PRMT / LOP3 / IADD3 / SEL), and the former byte-permuted
+// 24-bit index + bit-field decode put 7 such instructions on every pixel for the ~5 % that are exceptional.
+// tests/test_gpu_parity.py sweeps all 2^24 colours against the CPU oracle.
 #pragma once
 
 #include "hsv_exact.cuh"
@@ -50,6 +56,7 @@ struct CellCfg {
     float qscale;   // 2^QS
     u32 sat1_bits;  // bits of MAGIC + round(0.999999 * 2^QS)
     u32 full_val;   // 2^QS - 1: hue fraction of an edge pixel that counts as the END of its half bin
+    u32 hb_n;       // 2 * hp: half bins = entries per (max, min) pair of the exceptional-colour table
 };
 
 #define PHD_MAGIC_RN 12582912.0f   // 1.5 * 2^23: x + MAGIC has round(x) in its low mantissa bits (|x| < 2^22)
@@ -69,6 +76,7 @@ __device__ __forceinline__ CellCfg phd_cell_cfg(const DevParams& P, int qs) {
     c.qscale = (float)(1u << qs);
     c.sat1_bits = PHD_MAGIC_RN_BITS + (u32)__double2uint_rn(0.999999 * (double)(1u << qs));
     c.full_val = (1u << qs) - 1u;
+    c.hb_n = 2u * (u32)P.hp;
     return c;
 }
 
@@ -86,7 +94,15 @@ __device__ __forceinline__ float phd_rcp(float x) {
     return r;
 }
 
-// exc: the 2^24 exceptional-colour codes, indexed R | G << 8 | B << 16.
+// Exceptional-colour table: entry (t, k) -- t = tri(max) + min, k = half bin -- is two bytes at 2 * (t * 2hp + k).
+__host__ __device__ inline size_t phd_exc_bytes(int hp) { return (size_t)PHD_TRI_SIZE * 2 * (size_t)hp * 2; }
+// The pixel loop indexes the table with the half bin still carrying its float bias (the bits of 2^23 + k): kernels
+// pass phd_pixel the table pointer moved back by that bias once, instead of subtracting it per pixel.
+__device__ __forceinline__ const unsigned char* phd_exc_biased(const unsigned char* exc) {
+    return exc - 2ull * (unsigned long long)PHD_MAGIC_FLOOR_BITS;
+}
+
+// exc: the exceptional-colour table, biased (phd_exc_biased).
 __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned char* __restrict__ svtab,
                                             const CellCfg& K, const unsigned char* __restrict__ exc) {
     PixOut o;
@@ -99,7 +115,8 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
     const float pf = (float)p, qf = (float)q;
     float num2 = fmaf(120.0f, pf, offk * qf);          // 120 * (off*q + p), exact
     if (num2 < 0.0f) num2 = fmaf(720.0f, qf, num2);    // h < 0 -> h + 360 (:398-404)
-    const int cls = svtab[((mx * mx + mx) >> 1) + mn];
+    const int tri = ((mx * mx + mx) >> 1) + mn;
+    const int cls = svtab[tri];
     // half-bin index and exact remainder
     // Lh*q exactly for q >= 1 (the tiny addend rounds away); q == 0: num2 == 0 and any positive den gives half bin 0
     const float den = fmaf(K.Lh, qf, 1e-30f);
@@ -113,12 +130,11 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
     // cell = cls*4hp + 2*halfbin + 1, i.e. (cls*hp + (hb>>1))*4 + (hb odd ? 3 : 1)
     int cell = cls * K.hp4 + (int)(2u * __float_as_uint(hbm) + (1u - 2u * PHD_MAGIC_FLOOR_BITS));
     if (rem == 0.0f && q != 0) {
-        // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc);
-        // code = full << 7 | (cell delta + 4)
-        const u32 idx = __byte_perm(__byte_perm((u32)R, (u32)G, 0x1140), (u32)B, 0x3410);  // R | G << 8 | B << 16
-        const u32 code = __ldg(exc + idx);
-        cell += (int)(code & 0x7fu) - 4;
-        hbits = PHD_MAGIC_RN_BITS + (code >> 7) * K.full_val;
+        // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc).  frac == 0 here, so
+        // hbits == MAGIC_RN_BITS and the END of the half bin is one multiply-add away.
+        const unsigned char* e = exc + 2ull * (u32)((u32)tri * K.hb_n + __float_as_uint(hbm));
+        cell += (int)__ldg(reinterpret_cast<const signed char*>(e));
+        hbits += (u32)__ldg(e + 1) * K.full_val;
     }
     // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
     // (delta == max gives 2^QS, the clamp turns it into 0.999999; max == 0 gives 0 through the fmax)

@@ -288,12 +288,14 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
             bool below;
             if (b < 180.0) below = __dadd_rn(e.h, -b) < 0.0;               // t < 0 -> t + 360 (ends near 360)
             else below = !(__dadd_rn(e.h, __dsub_rn(360.0, b)) > 360.0);   // not wrapped (stays near 360)
+            // chunk-index delta (pixel_cells.cuh, CHUNK INDEX) relative to the ordinary ci = cls*4hp + k
+            const int to_rare = 2 * P.hp;  // same hue bin, from sub 1 (k even) to sub 0; one less: sub 2 of the bin below
             int delta, full = 0;
             if ((k & 1) == 0) {
                 const int dj = hi_ref - (k >> 1);
-                if (dj == 0) delta = below ? -1 : 0;  // (j, on the lower edge, low side) | (j, lower half)
-                else if (dj == -1 && k > 0) {         // (j-1, end of the upper half) | (j-1, on the upper edge)
-                    delta = below ? -2 : -3;
+                if (dj == 0) delta = below ? to_rare : 0;  // (j, on the lower edge, low side) | (j, lower half)
+                else if (dj == -1 && k > 0) {              // (j-1, end of the upper half) | (j-1, on the upper edge)
+                    delta = below ? -1 : to_rare - 1;
                     full = below ? 1 : 0;
                 } else {
                     delta = 0;
@@ -301,12 +303,12 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
                 }
             } else {
                 if (hi_ref != (k >> 1)) atomicAnd(ok, 0);
-                delta = below ? -2 : 0;  // (j, end of the lower half) | (j, upper half)
+                delta = below ? -1 : 0;  // (j, end of the lower half) | (j, upper half)
                 full = below ? 1 : 0;
             }
-            unsigned char* ent = out + 2 * ((size_t)(((mx * mx + mx) >> 1) + mn) * (2 * P.hp) + k);
-            ent[0] = (unsigned char)(signed char)delta;
-            ent[1] = (unsigned char)full;
+            unsigned char* ent = out + PHD_EXC_ENTRY * ((size_t)(((mx * mx + mx) >> 1) + mn) * (2 * P.hp) + k);
+            *reinterpret_cast<short*>(ent) = (short)delta;
+            ent[2] = (unsigned char)full;
         }
     }
 }

@@ -172,7 +172,7 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
     // (0 gray, 1 black) << 16 | (repairs wrapped all-black chunks) << 17.  Pairs that have a twin (top value bin of every
     // saturation bin, gray) sit together in the first warps and the others start at the next warp boundary, so that no
     // warp runs the twin drain for a few lanes only.
-    __shared__ uint2 dmeta[W3_THREADS];
+    __shared__ uint4 dmeta[W3_THREADS];  // z, w: chunk-index word offset (cls*4hp + 2j) of the pair and of its twin
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* base = rgb + (size_t)img * P.image_stride;
@@ -206,7 +206,9 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
             const int j = r - n_rest;
             d_pair = (spvp + 1) * hp + j; flags = 1u | (j == 0 ? 2u : 0u);
         }
-        dmeta[tid] = make_uint2(d_pair | (d_twin << 16), d_cc | (flags << 16));
+        auto src_of = [&](u32 pair) -> u32 { const u32 c = pair / (u32)hp; return c * 4u * (u32)hp + 2u * (pair - c * (u32)hp); };
+        dmeta[tid] = make_uint4(d_pair | (d_twin << 16), d_cc | (flags << 16), d_pair != 0xffff ? src_of(d_pair) : 0u,
+                                d_twin != 0xffff ? src_of(d_twin) : 0u);
     }
     {   // keep the table pointer in registers: the compiler would reload it from the constant bank per pixel
         unsigned long long e;
@@ -228,6 +230,8 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
         const int set = DB ? ((chunk - c_begin) & 1) : 0;
         const u32 cw_base = cw_base0 + (u32)set * set_b;
         const u32 scratch = cw_base + 4u * (u32)(NCW + lane);
+        // phd_pixel<true> leaves the float bias of the half bin in its chunk index: the base absorbs it (mod 2^32)
+        const u32 cw_ci = cw_base - 4u * PHD_MAGIC_FLOOR_BITS;
         const long long p0 = (long long)chunk * CHUNK + (long long)tid * 16;
         if (fast_ok && p0 + 16 <= P.hpx) {
             // PREFETCH: the next chunk's bytes are in flight (12 registers) while this one is processed; without it the
@@ -241,13 +245,13 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
             channel_sums(w, sum, sq);
             CellRun run;
             {
-                const PixOut o = phd_pixel(packed_byte(w, 0), packed_byte(w, 1), packed_byte(w, 2), svtab, K, exc);
-                run_start<4 * NCS, NW>(run, cw_base, o);
+                const PixOut o = phd_pixel<true>(packed_byte(w, 0), packed_byte(w, 1), packed_byte(w, 2), svtab, K, exc);
+                run_start<4 * NCS, NW>(run, cw_ci, o);
             }
 #pragma unroll kPixUnroll
             for (int i = 1; i < 16; i++)
-                run_step<4 * NCS, NW>(run, cw_base, scratch, stride_b,
-                                  phd_pixel(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1), packed_byte(w, 3 * i + 2),
+                run_step<4 * NCS, NW>(run, cw_ci, scratch, stride_b,
+                                  phd_pixel<true>(packed_byte(w, 3 * i), packed_byte(w, 3 * i + 1), packed_byte(w, 3 * i + 2),
                                             svtab, K, exc));
             run_emit<4 * NCS, NW>(run.addr, run, stride_b);
             if (more) {
@@ -267,12 +271,12 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
                     sum[0] += R; sum[1] += G; sum[2] += B;
                     sq[0] += R * R; sq[1] += G * G; sq[2] += B * B;
                 }
-                const PixOut o = phd_pixel(R, G, B, svtab, K, exc);
+                const PixOut o = phd_pixel<true>(R, G, B, svtab, K, exc);
                 if (!any) {
-                    run_start<4 * NCS, NW>(run, cw_base, o);
+                    run_start<4 * NCS, NW>(run, cw_ci, o);
                     any = true;
                 } else {
-                    run_step<4 * NCS, NW>(run, cw_base, scratch, stride_b, o);
+                    run_step<4 * NCS, NW>(run, cw_ci, scratch, stride_b, o);
                 }
             }
             if (any) run_emit<4 * NCS, NW>(run.addr, run, stride_b);
@@ -294,16 +298,23 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
             gb[set ^ 1][0] = 0; gb[set ^ 1][1] = 0;
         }
         // W3: (source pair of the chunk arrays, pair of the running sums it is added to, twin = its pixels have max 255)
+        // chunk words of a (class, hue bin) pair in the chunk-index layout (pixel_cells.cuh): the two ordinary half-bin
+        // cells (sub 1, 3) are the word pair at `src` (= cls*4hp + 2j), the two edge cells (sub 0, 2) the pair 2hp further
+        const int rare_off = 2 * hp;
+        auto ld_pair = [&](u32* arr, int src) -> uint4 {
+            const uint2 o = *reinterpret_cast<const uint2*>(arr + src), r = *reinterpret_cast<const uint2*>(arr + src + rare_off);
+            return make_uint4(r.x, o.x, r.y, o.y);
+        };
+        auto zero_pair = [&](u32* arr, int src) {
+            *reinterpret_cast<uint2*>(arr + src) = make_uint2(0, 0);
+            *reinterpret_cast<uint2*>(arr + src + rare_off) = make_uint2(0, 0);
+        };
         auto drain3 = [&](int src, int dst, bool twin) -> u32 {
-            uint4* ap = reinterpret_cast<uint4*>(cw) + src;
-            const uint4 a = *ap;
+            const uint4 a = ld_pair(cw, src);
             if ((a.x | a.y | a.z | a.w) == 0) return 0;
             saw = 1;
-            uint4* sp4 = reinterpret_cast<uint4*>(cw + ncs) + src;
-            uint4* hp4 = reinterpret_cast<uint4*>(cw + 2 * ncs) + src;
-            const uint4 sv = *sp4, hv = *hp4;
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            *ap = z; *sp4 = z; *hp4 = z;
+            const uint4 sv = ld_pair(cw + ncs, src), hv = ld_pair(cw + 2 * ncs, src);
+            zero_pair(cw, src); zero_pair(cw + ncs, src); zero_pair(cw + 2 * ncs, src);
             // count field; a cell that took the whole chunk wrapped it to 0 but kept its sum of max
             auto cnt = [](u32 w0) -> u32 { const u32 c = w0 >> 20; return (c == 0 && w0 != 0) ? (u32)CHUNK : c; };
             const uint4 n = make_uint4(cnt(a.x), cnt(a.y), cnt(a.z), cnt(a.w));
@@ -325,15 +336,11 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
         };
         // the four sub-cells of a (class, hue bin) pair are adjacent in every array: 16-byte accesses
         auto drain_pair = [&](int pair) -> u32 {
-            uint4* w0p = reinterpret_cast<uint4*>(cw) + pair;
-            const uint4 c = *w0p;
+            const int pc = pair / hp, src = pc * 4 * hp + 2 * (pair - pc * hp);
+            const uint4 c = ld_pair(cw, src);
             if ((c.x | c.y | c.z | c.w) == 0) return 0;
-            uint4* w1p = reinterpret_cast<uint4*>(cw + ncs) + pair;
-            uint4* w2p = reinterpret_cast<uint4*>(cw + 2 * ncs) + pair;
-            uint4* w3p = reinterpret_cast<uint4*>(cw + 3 * ncs) + pair;
-            const uint4 m = *w1p, sv = *w2p, hv = *w3p;
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            *w0p = z; *w1p = z; *w2p = z; *w3p = z;
+            const uint4 m = ld_pair(cw + ncs, src), sv = ld_pair(cw + 2 * ncs, src), hv = ld_pair(cw + 3 * ncs, src);
+            zero_pair(cw, src); zero_pair(cw + ncs, src); zero_pair(cw + 2 * ncs, src); zero_pair(cw + 3 * ncs, src);
             const uint4 n = make_uint4(c.x & 0xffffu, c.y & 0xffffu, c.z & 0xffffu, c.w & 0xffffu);
             uint4* ac = reinterpret_cast<uint4*>(acc_cnt) + pair;
             uint4* an = reinterpret_cast<uint4*>(acc_n255) + pair;
@@ -352,11 +359,11 @@ __device__ __forceinline__ void fe_walk(unsigned char* smem_raw, const uint8_t* 
         };
         if (W3) {
             // this thread's pair (see dmeta): read here so that nothing about it stays live through the pixel loop
-            const uint2 dm = dmeta[tid];
+            const uint4 dm = dmeta[tid];
             const int d_pair = (int)(dm.x & 0xffffu), d_twin = (int)(dm.x >> 16), d_cc = (int)(dm.y & 0xffffu);
             if (d_pair != 0xffff) {
-                u32 n = drain3(d_pair, d_pair, false);
-                if (d_twin != 0xffff) n += drain3(d_twin, d_pair, true);
+                u32 n = drain3((int)dm.z, d_pair, false);
+                if (d_twin != 0xffff) n += drain3((int)dm.w, d_pair, true);
                 if (d_cc != 0xffff) cc[d_cc] = (u16)n;
                 else if (n) atomicAdd(&gb[set][(dm.y >> 16) & 1u], n);
                 // the owner of the black pair of hue bin 0 repairs a wrapped all-black PREVIOUS chunk (see the barrier)

@@ -15,6 +15,14 @@
 //                     (so that cell = cls*4hp + 2*halfbin + 1 for every ordinary pixel)
 //     per cell: count, n(max==255), sum max, sum s*2^QS, sum (h - half-bin start)/(Lh/2)*2^QS
 //
+// CHUNK INDEX.  The pixel loop of the front end does not address its shared-memory chunk words by `cell` but by
+//     ci = cls * 4hp + hb                       ordinary pixels: hb = 2j + (upper half), i.e. sub 1 / 3
+//        = cls * 4hp + 2hp + 2j + (sub >> 1)    the rare edge cells, sub 0 / 2
+// so that the cells that take 95 % of the pixels are CONSECUTIVE words: with cell = 4 pair + sub they all sat in odd
+// words, i.e. the reductions of a warp shared 16 of the 32 banks (ncu: 23 M of 49 M shared-memory wavefronts of the
+// kernel were bank conflicts of the reductions, and the LSU data pipe was its top unit at 82 %).  phd_pixel<true>
+// returns ci, phd_pixel<false> the cell; phd_cell_from_ci converts.
+//
 // EXACTNESS.  hue = 60*(off + p/q) is a rational; the half-bin index is floor(num2/den) with num2 = 120*(off*q+p)
 // (+720q if negative), den = Lh*q, evaluated in FP32 on exactly representable integers (< 2^24) with a guard eps
 // that is far below the smallest possible distance 1/den of a non-integer quotient from an integer, and the
@@ -26,6 +34,7 @@
 // exceptional pixels only.  An exceptional colour is identified by (max, min, half bin) -- the hue k * Lh/2 fixes sector
 // and p, hence the third channel -- so the table is exc[tri(max, min)][2 hp] of TWO bytes: (cell delta, signed; 1 if the
 // hue fraction counts as the END of its half bin): 2.4 MB at 18 hue bins instead of a byte per 24-bit colour (16 MB),
+// (cell delta as a signed 16-bit chunk-index delta, flag: 4-byte entries, 4.7 MB),
 // indexed by two numbers the loop has anyway (the class-table index and the half bin), and applied with two
 // multiply-adds -- the pixel loop is bound by the ALU pipe (PRMT / LOP3 / IADD3 / SEL), and the former byte-permuted
 // 24-bit index + bit-field decode put 7 such instructions on every pixel for the ~5 % that are exceptional.
@@ -94,15 +103,25 @@ __device__ __forceinline__ float phd_rcp(float x) {
     return r;
 }
 
-// Exceptional-colour table: entry (t, k) -- t = tri(max) + min, k = half bin -- is two bytes at 2 * (t * 2hp + k).
-__host__ __device__ inline size_t phd_exc_bytes(int hp) { return (size_t)PHD_TRI_SIZE * 2 * (size_t)hp * 2; }
+// Exceptional-colour table: entry (t, k) -- t = tri(max) + min, k = half bin -- is four bytes at 4 * (t * 2hp + k):
+// s16 chunk-index delta (0, -1, 2hp, 2hp - 1), u8 "the hue fraction counts as the END of the half bin", one byte unused.
+#define PHD_EXC_ENTRY 4
+__host__ __device__ inline size_t phd_exc_bytes(int hp) { return (size_t)PHD_TRI_SIZE * 2 * (size_t)hp * PHD_EXC_ENTRY; }
 // The pixel loop indexes the table with the half bin still carrying its float bias (the bits of 2^23 + k): kernels
 // pass phd_pixel the table pointer moved back by that bias once, instead of subtracting it per pixel.
 __device__ __forceinline__ const unsigned char* phd_exc_biased(const unsigned char* exc) {
-    return exc - 2ull * (unsigned long long)PHD_MAGIC_FLOOR_BITS;
+    return exc - (unsigned long long)PHD_EXC_ENTRY * (unsigned long long)PHD_MAGIC_FLOOR_BITS;
 }
 
-// exc: the exceptional-colour table, biased (phd_exc_biased).
+// chunk index -> cell (see CHUNK INDEX above); cls is the class of ci (an exceptional pixel never leaves its class block)
+__device__ __forceinline__ int phd_cell_from_ci(int ci, int cls, int hp) {
+    const int r = ci - cls * 4 * hp;
+    const int rare = r >= 2 * hp ? 1 : 0, rr = r - rare * 2 * hp;  // rr = 2j + (sub >> 1)
+    return (cls * hp + (rr >> 1)) * 4 + 2 * (rr & 1) + 1 - rare;
+}
+
+// exc: the exceptional-colour table, biased (phd_exc_biased).  CI: o.cell is the chunk index ci instead of the cell.
+template <bool CI = false>
 __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned char* __restrict__ svtab,
                                             const CellCfg& K, const unsigned char* __restrict__ exc) {
     PixOut o;
@@ -127,20 +146,22 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
     const float rem = fmaf(-hbf, den, num2);           // exact: integers below 2^24
     const float frac = rem * rden;                     // in [0, 1)
     u32 hbits = __float_as_uint(fmaf(frac, K.qscale, PHD_MAGIC_RN));
-    // cell = cls*4hp + 2*halfbin + 1, i.e. (cls*hp + (hb>>1))*4 + (hb odd ? 3 : 1)
-    int cell = cls * K.hp4 + (int)(2u * __float_as_uint(hbm) + (1u - 2u * PHD_MAGIC_FLOOR_BITS));
+    // chunk index ci = cls*4hp + halfbin (the half bin still carries its float bias: removed below, or by the caller's
+    // base address when CI)
+    int cell = cls * K.hp4 + (int)__float_as_uint(hbm);
     if (rem == 0.0f && q != 0) {
         // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc).  frac == 0 here, so
         // hbits == MAGIC_RN_BITS and the END of the half bin is one multiply-add away.
-        const unsigned char* e = exc + 2ull * (u32)((u32)tri * K.hb_n + __float_as_uint(hbm));
-        cell += (int)__ldg(reinterpret_cast<const signed char*>(e));
-        hbits += (u32)__ldg(e + 1) * K.full_val;
+        const unsigned char* e = exc + (unsigned long long)PHD_EXC_ENTRY * (u32)((u32)tri * K.hb_n + __float_as_uint(hbm));
+        cell += (int)__ldg(reinterpret_cast<const short*>(e));
+        hbits += (u32)__ldg(e + 2) * K.full_val;
     }
     // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
     // (delta == max gives 2^QS, the clamp turns it into 0.999999; max == 0 gives 0 through the fmax)
     const u32 sraw = __float_as_uint(fmaf(qf * phd_rcp(fmaxf((float)mx, 1.0f)), K.qscale, PHD_MAGIC_RN));
     const u32 sbits = min(sraw, K.sat1_bits);
-    o.cell = cell;
+    // CI: ci + PHD_MAGIC_FLOOR_BITS (the caller's base address absorbs the bias); otherwise the cell
+    o.cell = CI ? cell : phd_cell_from_ci(cell - (int)PHD_MAGIC_FLOOR_BITS, cls, (int)(K.hb_n >> 1));
     o.w0 = (mx == 255) ? 0x10001u : 1u;
     o.mx = (u32)mx;
     o.sbits = sbits;

@@ -545,8 +545,9 @@ __device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, const voi
                  : "memory");
 }
 
-// TMA_OUT: the step's output (for every spectrum column k the 32 bytes specT[k][4q .. 4q+3]) is assembled as a tile in
-// shared memory (bufA is free after the last pass) and leaves through the TMA engine.  Written directly, every lane of
+// TMA_OUT: the step's output (for every spectrum column k the 32 bytes specT[k][4q .. 4q+3]) of the first `ktma` columns
+// is assembled as a tile in shared memory (the staging buffer is free after the last pass) and leaves through the TMA
+// engine; the other columns are stored directly.  Written directly, every lane of
 // a store instruction goes to a different 128-byte line: 961 lane-sectors per step through the LSU, whose data pipe is
 // the top unit of this kernel (ncu: 78 %); measured, the direct stores cost 2.3 of the kernel's 8.1 ms per 2048 1080p
 // images even when they are redirected to an L2-resident region, i.e. the cost is the requests, not the DRAM writes.
@@ -554,7 +555,8 @@ template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS, bool PR
 __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t* __restrict__ rgb, const DevParams& P,
                                           const float2* __restrict__ twp, float2* __restrict__ specT, const int img,
                                           const int q_begin, const int q_end, const int q_step,
-                                          const CUtensorMap* tmap = nullptr) {
+                                          const CUtensorMap* tmap = nullptr, const int ktma = 0,
+                                          const CUtensorMap* tmap_tail = nullptr) {
     constexpr int NP = N + N / 16;  // padded length
     // TMA_OUT: both buffers hold the padded layout and start on a 1 KB boundary (either can be the staging buffer, and
     // either can hold the swizzled output tile): the two swap roles every step, see below
@@ -613,6 +615,13 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
                     const float2 zk = z[pr * N + k], zc = z[pr * N + kc];
                     v[pr] = make_float4(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y), 0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
                 }
+                if (k >= ktma) {  // columns beyond the engine's share: straight to global memory
+                    float* o = reinterpret_cast<float*>(specT + (size_t)img * fw * P.Hp + 4 * q + (size_t)k * P.Hp);
+                    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(v[0].x), "f"(v[0].y),
+                                 "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z), "f"(v[1].w)
+                                 : "memory");
+                    continue;
+                }
                 float4* row = reinterpret_cast<float4*>(tile + 32 * k);
                 const int sw = (k >> 2) & 1;
                 row[sw] = v[0];
@@ -621,7 +630,10 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
             __syncthreads();
             if (threadIdx.x == 0) {
-                for (int k0 = 0; k0 < fw; k0 += 256) tma_store_box(tmap, tile + 32 * k0, 8 * q, k0, img);
+                // whole boxes of 256 columns, then the ktma % 256 remaining ones through a map whose box is that wide
+                int k0 = 0;
+                for (; k0 + 256 <= ktma; k0 += 256) tma_store_box(tmap, tile + 32 * k0, 8 * q, k0, img);
+                if (k0 < ktma) tma_store_box(tmap_tail, tile + 32 * k0, 8 * q, k0, img);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             float2* t = bufA; bufA = bufB; bufB = t;
@@ -667,10 +679,12 @@ __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 
 // the same walk with the TMA tensor store (tmap: rank 3 over specT, built by launch_rows_t)
 template <int N, int R0, int R1, int R2, int R3, int THREADS>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(rows_tma_smem(N), THREADS)) k_rows_tma(const uint8_t* __restrict__ rgb, DevParams P,
-                                                    const float2* __restrict__ twp, const __grid_constant__ CUtensorMap tmap) {
+                                                    const float2* __restrict__ twp, float2* __restrict__ specT,
+                                                    const __grid_constant__ CUtensorMap tmap,
+                                                    const __grid_constant__ CUtensorMap tmap_tail, int ktma) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    rows_walk<N, R0, R1, R2, R3, THREADS, 2, true, true>(smem_raw, rgb, P, twp, nullptr, blockIdx.y, blockIdx.x, P.H / 4,
-                                                          gridDim.x, &tmap);
+    rows_walk<N, R0, R1, R2, R3, THREADS, 2, true, true>(smem_raw, rgb, P, twp, specT, blockIdx.y, blockIdx.x, P.H / 4,
+                                                          gridDim.x, &tmap, ktma, &tmap_tail);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1256,7 +1270,7 @@ __global__ void __launch_bounds__(kColThreads) k_long_cols_epi(DevParams P, floa
 typedef CUresult (*PhdEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool make_spec_tmap(CUtensorMap* tm, float2* specT, const DevParams& P, int nimg) {
+bool make_spec_tmap(CUtensorMap* tm, float2* specT, const DevParams& P, int nimg, int box_cols) {
     static PhdEncodeTiled encode = []() -> PhdEncodeTiled {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
@@ -1269,10 +1283,12 @@ bool make_spec_tmap(CUtensorMap* tm, float2* specT, const DevParams& P, int nimg
     if (!encode) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)2 * P.Hp, (cuuint64_t)P.fw, (cuuint64_t)nimg};
     const cuuint64_t strides[2] = {(cuuint64_t)P.Hp * sizeof(float2), (cuuint64_t)P.fw * P.Hp * sizeof(float2)};
-    const cuuint32_t box[3] = {8, (cuuint32_t)(P.fw < 256 ? P.fw : 256), 1};
+    const cuuint32_t box[3] = {8, (cuuint32_t)box_cols, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, specT, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, specT, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (getenv("PHD_DEBUG")) fprintf(stderr, "[phd] spectrum tensor map (%d images, fw %d, Hp %d): %s\n", nimg, P.fw, P.Hp, rc == CUDA_SUCCESS ? "ok" : "REFUSED");
+    return rc == CUDA_SUCCESS;
 }
 
 // ---- dispatch tables of the specialised shapes -------------------------------------------------
@@ -1291,10 +1307,19 @@ void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float
     if (gx > nsteps) gx = nsteps;
     if (gx < 1) gx = 1;
     if constexpr (PAIRS == 2 && PHD_ROWS_TMA != 0) {
-        CUtensorMap tm;
-        if (make_spec_tmap(&tm, specT, P, nimg)) {
+        // How many spectrum columns leave through the engine; the rest is stored directly.  Measured at 1080p (961 columns,
+        // three CTAs per SM; ms per 2048 images): 0: 8.08, 256: 7.85, 512: 7.54, 768: 7.33, all: 7.3 .. 9.4 and erratic --
+        // with three CTAs feeding it 32-byte box rows the engine itself becomes the limit, so LSU and engine share the
+        // work (80 %, in whole boxes).  Rows of 3840 / 6000 pixels (one CTA per SM) are fastest with everything through
+        // the engine (4K: 15.9 -> 15.3 ms per 256 images; 24 MP: 20.7 with 2304 of 3001 columns, 20.0 with all).
+        static const int ktma_env = getenv("PHD_ROWS_KTMA") ? atoi(getenv("PHD_ROWS_KTMA")) : -1;
+        int ktma = rows_tma_smem(N) <= 110 * 1024 ? (P.fw * 4 / 5) / 256 * 256 : P.fw;
+        if (ktma_env >= 0) ktma = ktma_env < P.fw ? ktma_env : P.fw;
+        CUtensorMap tm, tm_tail;
+        if (ktma > 0 && make_spec_tmap(&tm, specT, P, nimg, 256) &&
+            make_spec_tmap(&tm_tail, specT, P, nimg, ktma % 256 ? ktma % 256 : 256)) {
             PHD_ALLOW_SMEM((k_rows_tma<N, R0, R1, R2, R3, THREADS>), rows_tma_smem(N));
-            k_rows_tma<N, R0, R1, R2, R3, THREADS><<<dim3(gx, nimg), THREADS, rows_tma_smem(N), st>>>(rgb, P, tw, tm);
+            k_rows_tma<N, R0, R1, R2, R3, THREADS><<<dim3(gx, nimg), THREADS, rows_tma_smem(N), st>>>(rgb, P, tw, specT, tm, tm_tail, ktma);
             return;
         }
     }

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) k_build_exc(DevParams P, unsigned char* _
             }
             unsigned char* ent = out + PHD_EXC_ENTRY * ((size_t)(((mx * mx + mx) >> 1) + mn) * (2 * P.hp) + k);
             *reinterpret_cast<short*>(ent) = (short)delta;
-            ent[2] = (unsigned char)full;
+            if (full != (delta == -1 ? 1 : 0)) atomicAnd(ok, 0);  // the table relies on "end of the half bin <=> delta == -1"
         }
     }
 }

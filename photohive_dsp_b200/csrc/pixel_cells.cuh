@@ -34,7 +34,7 @@
 // exceptional pixels only.  An exceptional colour is identified by (max, min, half bin) -- the hue k * Lh/2 fixes sector
 // and p, hence the third channel -- so the table is exc[tri(max, min)][2 hp] of TWO bytes: (cell delta, signed; 1 if the
 // hue fraction counts as the END of its half bin): 2.4 MB at 18 hue bins instead of a byte per 24-bit colour (16 MB),
-// (cell delta as a signed 16-bit chunk-index delta, flag: 4-byte entries, 4.7 MB),
+// (a signed 16-bit chunk-index delta: 2.4 MB),
 // indexed by two numbers the loop has anyway (the class-table index and the half bin), and applied with two
 // multiply-adds -- the pixel loop is bound by the ALU pipe (PRMT / LOP3 / IADD3 / SEL), and the former byte-permuted
 // 24-bit index + bit-field decode put 7 such instructions on every pixel for the ~5 % that are exceptional.
@@ -103,9 +103,12 @@ __device__ __forceinline__ float phd_rcp(float x) {
     return r;
 }
 
-// Exceptional-colour table: entry (t, k) -- t = tri(max) + min, k = half bin -- is four bytes at 4 * (t * 2hp + k):
-// s16 chunk-index delta (0, -1, 2hp, 2hp - 1), u8 "the hue fraction counts as the END of the half bin", one byte unused.
-#define PHD_EXC_ENTRY 4
+// Exceptional-colour table: entry (t, k) -- t = tri(max) + min, k = half bin -- is the s16 chunk-index delta at
+// 2 * (t * 2hp + k): 0, 2hp, 2hp - 1, or -1.  -1 (the pixel belongs to the half bin below) is also the one case in which
+// its hue fraction counts as the END of that half bin, so the table needs no second field -- and the pixel loop ONE load:
+// with two byte loads per exceptional pixel the loads alone (a few scattered lanes each, L2 latency) were ~12 % of the
+// kernel's LSU wavefronts.
+#define PHD_EXC_ENTRY 2
 __host__ __device__ inline size_t phd_exc_bytes(int hp) { return (size_t)PHD_TRI_SIZE * 2 * (size_t)hp * PHD_EXC_ENTRY; }
 // The pixel loop indexes the table with the half bin still carrying its float bias (the bits of 2^23 + k): kernels
 // pass phd_pixel the table pointer moved back by that bias once, instead of subtracting it per pixel.
@@ -153,8 +156,9 @@ __device__ __forceinline__ PixOut phd_pixel(int R, int G, int B, const unsigned 
         // exactly on a half-bin boundary: the reference's double rounding decides (k_build_exc).  frac == 0 here, so
         // hbits == MAGIC_RN_BITS and the END of the half bin is one multiply-add away.
         const unsigned char* e = exc + (unsigned long long)PHD_EXC_ENTRY * (u32)((u32)tri * K.hb_n + __float_as_uint(hbm));
-        cell += (int)__ldg(reinterpret_cast<const short*>(e));
-        hbits += (u32)__ldg(e + 2) * K.full_val;
+        const int delta = (int)__ldg(reinterpret_cast<const short*>(e));
+        cell += delta;
+        if (delta < 0) hbits += K.full_val;
     }
     // saturation (src/image_processing.c:412-414): 0 | 0.999999 | delta/max
     // (delta == max gives 2^QS, the clamp turns it into 0.999999; max == 0 gives 0 through the fmax)

@@ -65,6 +65,9 @@ if os.path.exists(rp):
             ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
             ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+            ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU data pipe % of peak"),
+            ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+            ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe %"),
             ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
             ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts")]
     lines += [f"## `ncu --set full --clock-control none` ({tag}): one launch each, {nimg_full}-image call (`tools/prof_driver.py {nimg_full}`)", ""]

@@ -41,7 +41,7 @@ print(f"`cuobjdump -sass`, architectures in the fatbin: {', '.join(arch)}.  One 
       "instantiations summed); columns are instruction counts in the machine code, not executed counts.\n")
 print("`UBLKCP` = cp.async.bulk (the TMA copy engine, 1-D), `SYNCS` = mbarrier operations, `FFMA2/FADD2/FMUL2` = packed FP32x2 "
       "(sm_100), `ATOMS` = shared-memory atomics, `REDG/ATOMG` = global reductions, `IDP` = dp2a/dp4a, `LDL/STL` = local-memory "
-      "(spill) accesses.  No `UTMALDG` (tensor-map TMA), `HMMA`/`UTC*MMA` (tensor cores) -- nothing here is a dense contraction.\n")
+      "(spill) accesses.  `UTMASTG` = cp.async.bulk.tensor store (tensor-map TMA: the row kernel's transposed output); no `UTMALDG`, `HMMA`/`UTC*MMA` (tensor cores) -- nothing here is a dense contraction.\n")
 print("| kernel family | instantiations | instructions | " + " | ".join(cols) + " |")
 print("|---|---|---|" + "---|" * len(cols))
 for f in sorted(ninst, key=lambda k: -ninst[k]):

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     u32* cbits = reinterpret_cast<u32*>(scnt + T);   // [(nchunks+31)/32] chunks the tie path must revisit
     int* scan_list = nmin;                           // [T] partly accepted tie groups (nmin[] is dead by then)
     __shared__ int sh_N, sh_nt, sh_nscan;
+    __shared__ int sh_wsum[32];
     __shared__ u64 sh_ssum;
 
     const double* gh = centres;
@@ -118,8 +119,15 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
 
     // Fast path: when every pair of saliencies is either equal or at least 1 apart and nothing can overflow
     // the float->int truncation, the reference's comparator is a strict weak order and its insertion sort
-    // is the stable descending sort -- computed here as a parallel rank sort.  Otherwise (differences in
-    // (0,1), |values| >= 2^30, NaN) thread 0 replays the insertion sort step by step.
+    // is the stable descending sort -- computed here as a parallel rank sort.
+    // Differences in (0,1) but no overflow (every |value| < 2^30): the comparator sees two elements as "equal" exactly
+    // when their float difference is below 1 in magnitude.  Cut the value-sorted sequence into CHAINS at the gaps >= 1:
+    // an element passes every element of a lower chain and stops at every element of a higher one (float subtraction is
+    // monotone), so the insertion sort's result is the chains in value order, and inside a chain whatever the insertion
+    // sort makes of the chain's members alone, inserted in index order.  Only chains with a gap in (0,1) differ from
+    // the rank sort, they are short, and one thread each replays them (fine palettes made most images take the serial
+    // replay: 15 of 84 ms per 4096 images of BASELINE config 5).
+    // Anything else (|values| >= 2^30, NaN, a chain longer than kMaxChain): one warp replays the whole insertion sort.
     int* rank = first;  // scratch, reused below
     for (int g = tid; g < T; g += blockDim.x) {
         const float sg = sal[g];
@@ -133,16 +141,59 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
     __syncthreads();
     for (int g = tid; g < T; g += blockDim.x) ids[rank[g]] = g;
     __syncthreads();
-    int ok = 1;
+    constexpr int kMaxChain = 48;
+    int ok = 1, no_ovf = 1;
     for (int i = tid; i < T; i += blockDim.x) {
         const float a = sal[ids[i]];
-        if (!(fabsf(a) < 1073741824.0f)) ok = 0;
+        if (!(fabsf(a) < 1073741824.0f)) { ok = 0; no_ovf = 0; }
         if (i + 1 < T) {
             const float d = __fsub_rn(a, sal[ids[i + 1]]);
             if (!(d == 0.0f || d >= 1.0f)) ok = 0;
         }
     }
-    const int safe = __syncthreads_and(ok);
+    int safe = __syncthreads_and(ok);
+    if (!safe && __syncthreads_and(no_ovf)) {
+        // chain repair: the thread at a chain's first position walks it, and replays it if it has a gap in (0,1)
+        int* order = nmin;  // scratch [T] (dead until the nearest-parent step): the repaired ids of the chains
+        int fail = 0;
+        for (int i = tid; i < T; i += blockDim.x) order[i] = ids[i];
+        __syncthreads();  // the chain threads below overwrite their members' entries
+        for (int i = tid; i < T; i += blockDim.x) {
+            if (i > 0 && !(__fsub_rn(sal[ids[i - 1]], sal[ids[i]]) >= 1.0f)) continue;  // not a chain start
+            int e = i + 1;
+            bool inner = false;
+            while (e < T) {
+                const float d = __fsub_rn(sal[ids[e - 1]], sal[ids[e]]);
+                if (d >= 1.0f) break;
+                inner = inner || d != 0.0f;
+                e++;
+            }
+            if (!inner) continue;  // all equal: the rank sort's index order is what the insertion sort gives
+            const int m = e - i;
+            if (m > kMaxChain) { fail = 1; continue; }
+            int mem[kMaxChain], out[kMaxChain];
+            for (int k = 0; k < m; k++) {  // members by ascending group index = insertion order
+                const int x = ids[i + k];
+                int pos = k;
+                while (pos > 0 && mem[pos - 1] > x) { mem[pos] = mem[pos - 1]; pos--; }
+                mem[pos] = x;
+            }
+            for (int k = 0; k < m; k++) {
+                const int x = mem[k];
+                const float v = sal[x];
+                int pos = k;
+                while (pos > 0 && trunc_f2i_x86(__fsub_rn(sal[out[pos - 1]], v)) < 0) { out[pos] = out[pos - 1]; pos--; }
+                out[pos] = x;
+            }
+            for (int k = 0; k < m; k++) order[i + k] = out[k];
+        }
+        const int any_fail = __syncthreads_or(fail);
+        if (!any_fail) {
+            for (int i = tid; i < T; i += blockDim.x) ids[i] = order[i];
+            safe = 1;
+        }
+        __syncthreads();
+    }
     if (!safe) {
         for (int g = tid; g < T; g += blockDim.x) ids[g] = g;
         __syncthreads();
@@ -179,42 +230,75 @@ __global__ void __launch_bounds__(256) k_palette_select(DevParams P, const doubl
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int goal = (int)((double)P.hpx * P.coverage);
-        int N = 0;
-        for (int i = 0; i < T; i++) {
-            goal -= n[ids[i]];
-            if (goal <= 0) { N = i + 1; break; }
+    // Parents: the first N groups in sorted order whose pixel counts reach the coverage goal (:342-360: goal -= count
+    // until goal <= 0).  A block-wide prefix sum over contiguous pieces of the sorted order instead of one thread's walk
+    // (871 dependent shared-memory loads with the fine palette, the other seven warps waiting at the barrier).
+    // coverage_thresh > 1 never reaches the goal in the reference (it then reads an unset array); every group becomes a
+    // parent here instead (sh_N starts at T).
+    {
+        const int goal = (int)((double)P.hpx * P.coverage);
+        const int per = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int i0 = min(tid * per, T), i1 = min(i0 + per, T);
+        int local = 0;
+        for (int i = i0; i < i1; i++) local += n[ids[i]];
+        const int lane = tid & 31, wid = tid >> 5;
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        // coverage_thresh > 1 never reaches the goal in the reference (it then reads an unset array);
-        // every group becomes a parent here instead.
-        if (N == 0) N = T;
-        sh_N = N;
-        for (int j = 0; j < N; j++) {
-            slot[ids[j]] = j;
-            const int pn = n[ids[j]];
-            fill[j] = pn > 0 ? ((pn - 1) % P.L) + 1 : 0;
-            pend[j] = -1;
-            scnt[j] = pn;
+        if (tid == 0) sh_N = T;
+        if (lane == 31) sh_wsum[wid] = incl;
+        __syncthreads();
+        int before = incl - local;
+        for (int w = 0; w < wid; w++) before += sh_wsum[w];
+        int cum = before;
+        for (int i = i0; i < i1; i++) {
+            cum += n[ids[i]];
+            if (cum >= goal) { atomicMin(&sh_N, i + 1); break; }
         }
+        __syncthreads();
+    }
+    const int N = sh_N;
+    for (int j = tid; j < N; j += blockDim.x) {
+        slot[ids[j]] = j;
+        const int pn = n[ids[j]];
+        fill[j] = pn > 0 ? ((pn - 1) % P.L) + 1 : 0;
+        pend[j] = -1;
+        scnt[j] = pn;
     }
     __syncthreads();
-    const int N = sh_N;
 
-    // nearest parent(s) of every non-empty non-parent group
-    for (int g = tid; g < T; g += blockDim.x) {
-        first[g] = -1;
-        nmin[g] = 0;
-        if (n[g] == 0 || slot[g] >= 0) continue;
-        double m = (double)T * (double)T;
-        int cnt = 0, fi = -1;
-        for (int j = 0; j < N; j++) {
-            const double d = centre_dist(gh, gs, gv, T, P.vp, g, ids[j]);
-            if (d < m) { m = d; cnt = 1; fi = j; }
-            else if (d == m) cnt++;
+    // nearest parent(s) of every non-empty non-parent group (:370-392): the smallest distance, how many parents are at
+    // exactly that distance, and the first of them in parent order.  One WARP per group, the parents spread over its lanes
+    // (a thread per group left most threads idle -- few groups need the search, each needs all N parents in FP64).
+    {
+        const int lane = tid & 31, wid = tid >> 5, nwarps = (int)blockDim.x >> 5;
+        for (int g = wid; g < T; g += nwarps) {
+            if (n[g] == 0 || slot[g] >= 0) {
+                if (lane == 0) { first[g] = -1; nmin[g] = 0; }
+                continue;
+            }
+            double m = (double)T * (double)T;
+            int cnt = 0, fi = 0x7fffffff;
+            for (int j = lane; j < N; j += 32) {
+                const double d = centre_dist(gh, gs, gv, T, P.vp, g, ids[j]);
+                if (d < m) { m = d; cnt = 1; fi = j; }
+                else if (d == m) cnt++;
+            }
+            // the warp's minimum; lanes that hold it contribute their counts and their first index
+            double wm = m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wm = fmin(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+            int c = (cnt > 0 && m == wm) ? cnt : 0, f = (cnt > 0 && m == wm) ? fi : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c += __shfl_xor_sync(0xffffffffu, c, o);
+                f = min(f, __shfl_xor_sync(0xffffffffu, f, o));
+            }
+            if (lane == 0) { first[g] = c > 0 ? f : -1; nmin[g] = c; }
         }
-        first[g] = fi;
-        nmin[g] = cnt;
     }
     __syncthreads();
 

@@ -69,6 +69,12 @@ def test_report_matches_reference_golden(ctx, oracle, golden, name):
     # saliencies closer than 1 apart: the truncating comparator calls them equal (insertion-sort replay)
     (800, 600, 0, dict(quantity_weight=0.0, saturation_value_weight=1e-5)),
     (800, 600, 1, dict(quantity_weight=1e-6, saturation_value_weight=1e-6, coverage_thresh=0.5)),
+    # saliencies a fraction of a pixel count apart: many short chains of "equal" neighbours (chain repair of
+    # k_palette_select), also with the fine palette's 871 groups
+    (800, 600, 0, dict(quantity_weight=3.7e-4, saturation_value_weight=2.3e-4)),
+    (800, 600, 1, dict(quantity_weight=1.3e-3, saturation_value_weight=4.1e-4, coverage_thresh=0.9)),
+    (800, 600, 0, dict(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99, quantity_weight=2.9e-3,
+                       saturation_value_weight=1.7e-3)),
     # saliencies beyond 2^31: the float->int conversion overflows to INT_MIN
     (800, 600, 0, dict(quantity_weight=30000.0, saturation_value_weight=50000.0)),
     (640, 480, 2, dict(h_partitions=36, s_partitions=4, v_partitions=6, coverage_thresh=0.99, linked_list_size=3)),

@@ -272,7 +272,9 @@ __device__ __forceinline__ float2 cmul2(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-template <int N, int R, int S, bool PADIN, int GT, bool PK, bool TWPOW = false>
+// OPAD / IPAD: the output of this pass is skewed by OPAD elements per block of R*S outputs, the input of this pass was
+// written with such a skew of IPAD per sub-sequence (see fft_skew).
+template <int N, int R, int S, bool PADIN, int GT, bool PK, bool TWPOW = false, int OPAD = 0, int IPAD = 0>
 __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
                                        const float2* __restrict__ twp, int nfft, int fstride_in, int fstride_out) {
     constexpr int M = N / R;
@@ -296,9 +298,10 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
             for (int k = 0; k < R; k++) x[k] = a[b0 + k * (M + M / 16)];
         } else {
 #pragma unroll
-            for (int k = 0; k < R; k++) x[k] = a[b + k * M];
+            for (int k = 0; k < R; k++) x[k] = a[b + k * (M + IPAD)];
         }
         Radix<R, PK>::run(x);
+        if (OPAD > 0) y += OPAD * (b / S);
         if (S * R == N) {  // last pass: every twiddle is 1
 #pragma unroll
             for (int j = 0; j < R; j++) y[q + j * S] = x[j];
@@ -325,6 +328,17 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
 // whole passes, so a sequence must never be written into another sequence's region of either buffer.
 // Returns the buffer holding the result (unpadded; stride fstride for b, fstride_a for a).  The barrier after the
 // LAST pass is left to the caller (it usually needs a CTA-wide one there anyway).
+// Skew of the second pass's output.  Consecutive butterflies b of that pass write consecutive elements q = b % R0 of one
+// block of R0*R1 outputs and then jump to the next block: in a half warp (8-byte accesses) the lane after the jump lands
+// on the bank pair of an earlier lane unless the block stride is congruent to R0 modulo 16 -- two-way conflicts on every
+// store of the pass (ncu: 11 % of the row kernel's shared-memory wavefronts).  The third pass reads sub-sequence k at
+// k * (N / R2) = k * R0 * R1, i.e. exactly those blocks, so skewing every block by `fft_skew` elements costs nothing on
+// the reading side.  Only where the buffer has the room: the padded staging layout (N / 16 spare elements).
+__host__ __device__ constexpr int fft_skew(int n, int r0, int r1, int r2, bool padin) {
+    const int p = (((r0 * (1 - r1)) % 16) + 16) % 16;
+    return (padin && p * (r2 - 1) <= n / 16) ? p : 0;
+}
+
 template <int N, int R0, int R1, int R2, int R3, bool PADIN, int GT, bool PK, bool TWPOW = false>
 __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2* __restrict__ twp, int nfft,
                                              int fstride_a, int fstride) {
@@ -332,9 +346,10 @@ __device__ __forceinline__ float2* fft_run_t(float2* a, float2* b, const float2*
     using PL = PlanT<N, R0, R1, R2, R3>;
     pass_t<N, R0, 1, PADIN, GT, PK, TWPOW>(a, b, twp + PL::off0, nfft, fstride_a, fstride);
     seq_sync<GT>();
-    pass_t<N, R1, R0, false, GT, PK, TWPOW>(b, a, twp + PL::off1, nfft, fstride, fstride_a);
+    constexpr int SKEW = R3 == 1 ? fft_skew(N, R0, R1, R2, PADIN) : 0;
+    pass_t<N, R1, R0, false, GT, PK, TWPOW, SKEW>(b, a, twp + PL::off1, nfft, fstride, fstride_a);
     seq_sync<GT>();
-    pass_t<N, R2, R0 * R1, false, GT, PK>(a, b, twp + PL::off2, nfft, fstride_a, fstride);
+    pass_t<N, R2, R0 * R1, false, GT, PK, false, 0, SKEW>(a, b, twp + PL::off2, nfft, fstride_a, fstride);
     if (R3 == 1) return b;
     seq_sync<GT>();
     pass_t<N, (R3 == 1 ? 2 : R3), (R3 == 1 ? N / 2 : R0 * R1 * R2), false, GT, PK>(b, a, twp + PL::off3, nfft, fstride, fstride_a);

@@ -182,6 +182,29 @@ def test_device_resident_input_equals_host_input(ctx, oracle):
     assert np.array_equal(host.raw, dev.raw)
 
 
+@pytest.mark.parametrize("env", [{"PHD_NO_TMA_STORE": "1"}, {"PHD_ROWS_KTMA": "256"}, {"PHD_ROWS_KTMA": "100000"}])
+@pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160), (640, 480)])
+def test_row_output_paths_give_identical_records(ctx, oracle, env, W, H):
+    """The row kernel's transposed spectrum leaves through a TMA tensor store, through direct stores, or split between
+    them (fft.cu, rows_walk); which path takes which spectrum column must not change a single bit of a record.  The
+    choice is read once per process, so the other paths run in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, zlib, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from oracle.binding import Oracle\n"
+        "from photohive_dsp_b200.batch import Context\n"
+        f"imgs = np.stack([Oracle().generate(k % 3, 77 + k, {W}, {H}) for k in range(3)])\n"
+        "print(zlib.crc32(Context(0).get_reports(imgs).raw.tobytes()))\n")
+    imgs = np.stack([oracle.generate(k % 3, 77 + k, W, H) for k in range(3)])
+    want = zlib.crc32(ctx.get_reports(imgs).raw.tobytes())
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert int(out.stdout.strip().splitlines()[-1]) == want, env
+
+
 def test_two_devices_in_one_process(ctx, oracle):
     """One context per GPU inside ONE process (the library allows it): same records from both devices."""
     import torch

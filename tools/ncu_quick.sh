@@ -11,7 +11,7 @@ smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_w
 smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,\
 smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__sass_inst_executed_op_shared_ld.sum,smsp__sass_inst_executed_op_shared_st.sum,\
 smsp__inst_executed_op_shared_atom.sum,smsp__sass_inst_executed_op_global_ld.sum
-ncu --metrics $M --clock-control none -k regex:"$2" -c 1 --csv --log-file gpurun_out/$1_quick.csv python tools/prof_driver.py 32 > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:"$2" -c 1 --csv --log-file gpurun_out/$1_quick.csv python tools/prof_driver.py ${3:-32} $4 $5 > /dev/null 2>&1
 python - <<P
 import csv
 rows = [r for r in csv.reader(open("gpurun_out/$1_quick.csv")) if len(r) > 10]

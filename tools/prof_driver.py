@@ -1,4 +1,5 @@
-"""Small fixed workload for ncu: 32 device-resident 1080p images (G0/G1), default parameters, two calls."""
+"""Small fixed workload for ncu: N device-resident images (G0/G1; 1080p unless W H are given), default parameters, two calls.
+  python tools/prof_driver.py [N=32] [W H]"""
 import os
 import sys
 
@@ -10,7 +11,7 @@ from photohive_dsp_b200.batch import Context, flat_layout, make_params  # noqa: 
 from tools.synth import Generator  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-W, H = 1920, 1080
+W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080)
 dev = torch.device("cuda", 0)
 ctx = Context(0)
 p = make_params()

@@ -374,8 +374,18 @@ __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* _
         for (int k = 0; k < R; k++) x[k] = a[b + k * m];
         Radix<R, false>::run(x);
         y[R * pps + q] = x[0];
+        if (PHD_ROWS_TWPOW != 0) {  // twiddles of the butterfly from its first table entry (see pass_t)
+            float2 w[R];
+            w[1] = __ldg(&twp[b]);
 #pragma unroll
-        for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf<false>(x[j], __ldg(&twp[(j - 1) * m + b]));
+            for (int j = 1; j < R; j++) {
+                if (j > 1) w[j] = (j % 2 == 0) ? csqr(w[j / 2]) : cmul2(w[j - 1], w[1]);
+                y[R * pps + q + j * s] = cmulf<false>(x[j], w[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 1; j < R; j++) y[R * pps + q + j * s] = cmulf<false>(x[j], __ldg(&twp[(j - 1) * m + b]));
+        }
     }
 }
 

@@ -812,7 +812,29 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
             }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < NP * W; idx += blockDim.x) {
+        // Four pixels per task where the row allows it (width and row bytes multiples of 4, bytes not a float plane):
+        // three aligned words per row instead of twelve byte loads -- the staged compile-time widths (1080, 3000, ...:
+        // portrait video and photos) spent more LSU wavefronts on this conversion than on a pass of the transform.
+        const bool quad = !gray32 && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) | (uintptr_t)row_bytes) % 4 == 0);
+        for (int idx = threadIdx.x; quad && idx < NP * (W / 4); idx += blockDim.x) {
+            const int pair = idx / (W / 4), x4 = idx - pair * (W / 4);
+            int g[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = 2 * NP * q + 2 * pair + h;
+                const u32* pw = reinterpret_cast<const u32*>(raw + (size_t)(2 * pair + h) * row_bytes) + 3 * x4;
+                const u32 a = pw[0], b = pw[1], c = pw[2];  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+                const bool in = row < P.H;
+                g[h][0] = in ? 299 * (int)(a & 255u) + 587 * (int)((a >> 8) & 255u) + 114 * (int)((a >> 16) & 255u) - PHD_GRAY_BIAS : 0;
+                g[h][1] = in ? 299 * (int)(a >> 24) + 587 * (int)(b & 255u) + 114 * (int)((b >> 8) & 255u) - PHD_GRAY_BIAS : 0;
+                g[h][2] = in ? 299 * (int)((b >> 16) & 255u) + 587 * (int)(b >> 24) + 114 * (int)(c & 255u) - PHD_GRAY_BIAS : 0;
+                g[h][3] = in ? 299 * (int)((c >> 8) & 255u) + 587 * (int)((c >> 16) & 255u) + 114 * (int)(c >> 24) - PHD_GRAY_BIAS : 0;
+            }
+            float2* dst = bufA + pair * L + 4 * x4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) dst[i] = make_float2((float)g[0][i], (float)g[1][i]);
+        }
+        for (int idx = threadIdx.x; !quad && idx < NP * W; idx += blockDim.x) {
             const int pair = idx / W, x = idx - pair * W;
             int g[2];
 #pragma unroll
@@ -832,6 +854,7 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
         __syncthreads();
         const float2* z;
         if constexpr (N > 0) {
+            // table twiddles here: the product tree measured slower in this variant (3000-pixel rows 55 -> 84 us per image)
             z = fft_run_t<N, R0, R1, R2, 1, false, THREADS / NP, false>(bufA, bufB, pl.twp, NP, N, N);
             __syncthreads();
         } else {

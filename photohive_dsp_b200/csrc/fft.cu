@@ -278,7 +278,7 @@ template <int N, int R, int S, bool PADIN, int GT, bool PK, bool TWPOW = false, 
 __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __restrict__ out,
                                        const float2* __restrict__ twp, int nfft, int fstride_in, int fstride_out) {
     constexpr int M = N / R;
-    static_assert(!PADIN || M % 16 == 0, "padded input needs M % 16 == 0");
+    // padded input: with M % 16 == 0 the pad of b + k * M splits into pad16(b) + k * (M + M / 16); otherwise per element
     const int total = GT > 0 ? M : nfft * M;
     const int first = GT > 0 ? (int)threadIdx.x % GT : (int)threadIdx.x;
     const int step = GT > 0 ? GT : (int)blockDim.x;
@@ -293,9 +293,14 @@ __device__ __forceinline__ void pass_t(const float2* __restrict__ in, float2* __
         float2* y = out + f * fstride_out;
         float2 x[R];
         if (PADIN) {
-            const int b0 = pad16(b);
+            if constexpr (M % 16 == 0) {
+                const int b0 = pad16(b);
 #pragma unroll
-            for (int k = 0; k < R; k++) x[k] = a[b0 + k * (M + M / 16)];
+                for (int k = 0; k < R; k++) x[k] = a[b0 + k * (M + M / 16)];
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; k++) x[k] = a[pad16(b + k * M)];
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < R; k++) x[k] = a[b + k * (M + IPAD)];
@@ -532,7 +537,8 @@ __global__ void k_pass_twiddles(float2* out, int n, int r, int s) {
 
 // Gray numerator 299 R + 587 G + 114 B - 127500 of pixel i (0..15) of 48 packed bytes: two 2-way dot products
 // (16-bit weights x bytes, IDP.2A) straight on the packed words, whatever the pixel's byte alignment.
-__device__ __forceinline__ int gray16(const u32 (&w)[12], int i) {
+template <int NWORDS>
+__device__ __forceinline__ int gray16(const u32 (&w)[NWORDS], int i) {
     const int b = 3 * i, k = b >> 2, s = b & 3;
     const u32 bias = (u32)(-PHD_GRAY_BIAS);
     constexpr u32 RG = 299u | (587u << 16), B_ = 114u, _R = 299u << 16, GB = 587u | (114u << 16);
@@ -557,6 +563,13 @@ constexpr int rows_min_blocks(int smem_bytes, int threads) {
     return by_smem < by_regs ? by_smem : by_regs;
 }
 
+// The row kernel stages SEG pixels of a row pair per thread (rows_walk): 16 where width and first-pass sub-length are
+// multiples of 16, else 8 for widths that are a multiple of 8 (1080, 3000, 600, 1800: portrait video and photos).
+template <int N, int R0>
+constexpr int rows_seg() { return (N % 16 == 0 && (N / R0) % 16 == 0) ? 16 : 8; }
+template <int N, int R0>
+constexpr bool rows_t_ok() { return N % 8 == 0; }
+
 // shared memory of the row kernel with the TMA store: two buffers of two padded row pairs, each rounded up to 1 KB
 constexpr int rows_tma_smem(int n) { return 2 * ((2 * (n + n / 16) * 8 + 1023) / 1024 * 1024); }
 
@@ -576,7 +589,9 @@ __device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, const voi
 // a store instruction goes to a different 128-byte line: 961 lane-sectors per step through the LSU, whose data pipe is
 // the top unit of this kernel (ncu: 78 %); measured, the direct stores cost 2.3 of the kernel's 8.1 ms per 2048 1080p
 // images even when they are redirected to an L2-resident region, i.e. the cost is the requests, not the DRAM writes.
-template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS, bool PREFETCH = true, bool TMA_OUT = false>
+// SEG: pixels per staging task, 16 (three 16-byte loads per row) or 8 (three 8-byte loads: widths that are a multiple of 8
+// but not of 16, e.g. the 1080-pixel rows of portrait video -- rows then start on 8-byte boundaries only).
+template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS, bool PREFETCH = true, bool TMA_OUT = false, int SEG = 16>
 __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t* __restrict__ rgb, const DevParams& P,
                                           const float2* __restrict__ twp, float2* __restrict__ specT, const int img,
                                           const int q_begin, const int q_end, const int q_step,
@@ -592,21 +607,41 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
     // Per step: PAIRS row pairs x N/16 segments of 16 pixels; one task (thread) holds the segment of BOTH rows of
     // its pair (2 x three 16-byte loads).  The loads of the next step are issued before the passes of this one and
     // stay in registers meanwhile.
-    constexpr int SEGS = N / 16;
+    constexpr int SEGS = N / SEG;
+    static_assert(SEG == 16 || SEG == 8, "16 or 8 pixels per staging task");
+    static_assert(N % SEG == 0, "whole segments");
     static_assert(R3 == 1, "the output loop below reads the result with stride N (buffer b)");
     constexpr int GT = THREADS / PAIRS;  // threads of one pair: they stage, transform and synchronise among themselves
     static_assert(SEGS <= GT && GT % 32 == 0, "one staging task per thread of the pair's group");
     const int pair = threadIdx.x / GT, seg = threadIdx.x % GT;
     const bool has_task = seg < SEGS;
-    uint4 a0, b0, c0, a1, b1, c1;
+    constexpr int NWORDS = 3 * SEG / 4;  // packed words of a segment of one row
+    u32 w0[NWORDS], w1[NWORDS];
     auto load_step = [&](int q) {
         const uint8_t* base = img_base + (size_t)(2 * PAIRS * q) * N * 3;
-        const uint4* s0 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair) * N * 3 + (size_t)seg * 48);
-        const uint4* s1 = reinterpret_cast<const uint4*>(base + (size_t)(2 * pair + 1) * N * 3 + (size_t)seg * 48);
-        // plain cached loads: the three 16-byte pieces of neighbouring threads share 128-byte lines, and loads that
-        // bypass L1 (ld.global.nc.L1::no_allocate) measured 20 % slower for the whole kernel
-        a0 = __ldg(s0); b0 = __ldg(s0 + 1); c0 = __ldg(s0 + 2);
-        a1 = __ldg(s1); b1 = __ldg(s1 + 1); c1 = __ldg(s1 + 2);
+        const uint8_t* p0 = base + (size_t)(2 * pair) * N * 3 + (size_t)seg * (3 * SEG);
+        const uint8_t* p1 = base + (size_t)(2 * pair + 1) * N * 3 + (size_t)seg * (3 * SEG);
+        // plain cached loads: the three pieces of neighbouring threads share 128-byte lines, and loads that bypass L1
+        // (ld.global.nc.L1::no_allocate) measured 20 % slower for the whole kernel
+        if constexpr (SEG == 16) {
+            const uint4* s0 = reinterpret_cast<const uint4*>(p0);
+            const uint4* s1 = reinterpret_cast<const uint4*>(p1);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const uint4 a = __ldg(s0 + j), b = __ldg(s1 + j);
+                w0[4 * j] = a.x; w0[4 * j + 1] = a.y; w0[4 * j + 2] = a.z; w0[4 * j + 3] = a.w;
+                w1[4 * j] = b.x; w1[4 * j + 1] = b.y; w1[4 * j + 2] = b.z; w1[4 * j + 3] = b.w;
+            }
+        } else {
+            const uint2* s0 = reinterpret_cast<const uint2*>(p0);
+            const uint2* s1 = reinterpret_cast<const uint2*>(p1);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const uint2 a = __ldg(s0 + j), b = __ldg(s1 + j);
+                w0[2 * j] = a.x; w0[2 * j + 1] = a.y;
+                w1[2 * j] = b.x; w1[2 * j + 1] = b.y;
+            }
+        }
     };
     if (PREFETCH && has_task && q_begin < q_end) load_step(q_begin);
     const int fw = N / 2 + 1;
@@ -614,11 +649,9 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
     for (int q = q_begin; q < q_end; q += q_step) {
         if (has_task) {
             if (!PREFETCH) load_step(q);  // no registers held across the passes (fused kernel)
-            const u32 w0[12] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w, c0.x, c0.y, c0.z, c0.w};
-            const u32 w1[12] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w, c1.x, c1.y, c1.z, c1.w};
-            float2* dst = bufA + pair * NP + seg * 17;
+            float2* dst = bufA + pair * NP + pad16(seg * SEG);  // a segment never straddles a pad (16 | seg * SEG, or 8-runs)
 #pragma unroll
-            for (int i = 0; i < 16; i++) dst[i] = make_float2((float)gray16(w0, i), (float)gray16(w1, i));
+            for (int i = 0; i < SEG; i++) dst[i] = make_float2((float)gray16(w0, i), (float)gray16(w1, i));
             if (PREFETCH && q + q_step < q_end) load_step(q + q_step);
         }
         // TMA_OUT: the first pass writes bufB, which holds the previous step's output tile: the engine must have read it.
@@ -692,24 +725,24 @@ __device__ __forceinline__ void rows_walk(unsigned char* smem_raw, const uint8_t
     if (TMA_OUT && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS>
+template <int N, int R0, int R1, int R2, int R3, int THREADS, int PAIRS, int SEG = 16>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(PAIRS * (2 * N + N / 16) * 8, THREADS)) k_rows_t(const uint8_t* __restrict__ rgb, DevParams P,
                                                     const float2* __restrict__ twp, float2* __restrict__ specT) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // steps blockIdx.x, blockIdx.x + gridDim.x, ...: CTAs that run together work on neighbouring rows, so the
     // pieces they write into the same 128-byte lines of the transposed spectrum meet in L2
-    rows_walk<N, R0, R1, R2, R3, THREADS, PAIRS>(smem_raw, rgb, P, twp, specT, blockIdx.y, blockIdx.x, P.H / (2 * PAIRS),
-                                                 gridDim.x);
+    rows_walk<N, R0, R1, R2, R3, THREADS, PAIRS, true, false, SEG>(smem_raw, rgb, P, twp, specT, blockIdx.y, blockIdx.x,
+                                                                   P.H / (2 * PAIRS), gridDim.x);
 }
 // the same walk with the TMA tensor store (tmap: rank 3 over specT, built by launch_rows_t)
-template <int N, int R0, int R1, int R2, int R3, int THREADS>
+template <int N, int R0, int R1, int R2, int R3, int THREADS, int SEG = 16>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(rows_tma_smem(N), THREADS)) k_rows_tma(const uint8_t* __restrict__ rgb, DevParams P,
                                                     const float2* __restrict__ twp, float2* __restrict__ specT,
                                                     const __grid_constant__ CUtensorMap tmap,
                                                     const __grid_constant__ CUtensorMap tmap_tail, int ktma) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    rows_walk<N, R0, R1, R2, R3, THREADS, 2, true, true>(smem_raw, rgb, P, twp, specT, blockIdx.y, blockIdx.x, P.H / 4,
-                                                          gridDim.x, &tmap, ktma, &tmap_tail);
+    rows_walk<N, R0, R1, R2, R3, THREADS, 2, true, true, SEG>(smem_raw, rgb, P, twp, specT, blockIdx.y, blockIdx.x, P.H / 4,
+                                                               gridDim.x, &tmap, ktma, &tmap_tail);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1342,9 +1375,10 @@ bool make_spec_tmap(CUtensorMap* tm, float2* specT, const DevParams& P, int nimg
 // ---- dispatch tables of the specialised shapes -------------------------------------------------
 template <int N, int R0, int R1, int R2, int R3, int PAIRS>
 void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
-    constexpr int THREADS = ((PAIRS * (N / 16) + 127) / 128) * 128;  // one 16-pixel staging task per thread
+    constexpr int SEG = rows_seg<N, R0>();
+    constexpr int THREADS = ((PAIRS * (N / SEG) + 127) / 128) * 128;  // one staging task (SEG pixels of a row pair) per thread
     const size_t smem = (size_t)PAIRS * (2 * N + N / 16) * sizeof(float2);
-    PHD_ALLOW_SMEM((k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS>), (int)smem);
+    PHD_ALLOW_SMEM((k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS, SEG>), (int)smem);
     // CTAs walk strided steps.  gx CTAs per image: the launch runs in ceil(gx * nimg / resident) waves of
     // ceil(nsteps / gx) steps (+ about one step's worth of start-up per CTA: the first loads are not prefetched); pick
     // the gx that minimises that product.  One CTA per image -- what "about four waves in all" gave for large batches --
@@ -1375,12 +1409,12 @@ void launch_rows_t(const uint8_t* rgb, const DevParams& P, int nimg, const float
         CUtensorMap tm, tm_tail;
         if (ktma > 0 && make_spec_tmap(&tm, specT, P, nimg, 256) &&
             make_spec_tmap(&tm_tail, specT, P, nimg, ktma % 256 ? ktma % 256 : 256)) {
-            PHD_ALLOW_SMEM((k_rows_tma<N, R0, R1, R2, R3, THREADS>), rows_tma_smem(N));
-            k_rows_tma<N, R0, R1, R2, R3, THREADS><<<dim3(gx, nimg), THREADS, rows_tma_smem(N), st>>>(rgb, P, tw, specT, tm, tm_tail, ktma);
+            PHD_ALLOW_SMEM((k_rows_tma<N, R0, R1, R2, R3, THREADS, SEG>), rows_tma_smem(N));
+            k_rows_tma<N, R0, R1, R2, R3, THREADS, SEG><<<dim3(gx, nimg), THREADS, rows_tma_smem(N), st>>>(rgb, P, tw, specT, tm, tm_tail, ktma);
             return;
         }
     }
-    k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS><<<dim3(gx, nimg), THREADS, smem, st>>>(rgb, P, tw, specT);
+    k_rows_t<N, R0, R1, R2, R3, THREADS, PAIRS, SEG><<<dim3(gx, nimg), THREADS, smem, st>>>(rgb, P, tw, specT);
 }
 
 template <int N, int R0, int R1, int R2, int R3, int NB, int MINB = 2>
@@ -1543,9 +1577,7 @@ void phd_fill_twiddles(float2* dev_tw, int n, cudaStream_t st) {
     k_twiddles<<<(n + 255) / 256, 256, 0, st>>>(dev_tw, n);
 }
 
-// The row kernel stages 16 pixels per thread and pads every 16 elements: only lengths that allow it are instantiated.
-template <int N, int R0>
-constexpr bool rows_t_ok() { return N % 16 == 0 && (N / R0) % 16 == 0; }
+// (rows_t_ok / rows_seg: which lengths the row kernel takes, and with which staging granularity -- defined above)
 template <int N, int R0, int R1, int R2>
 static void launch_rows_t_if(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
     if constexpr (rows_t_ok<N, R0>()) launch_rows_t<N, R0, R1, R2, 1, 2>(rgb, P, nimg, tw, specT, st);
@@ -1580,7 +1612,7 @@ static void launch_rows_staged_if(const uint8_t* rgb, const DevParams& P, int ni
 // Lengths the fused front-end + row kernel is built for: the row role must fit the front end's CTA (256 threads, i.e.
 // at most 128 sixteen-pixel segments per row, two row pairs) and its shared memory (three CTAs per SM).
 template <int N, int R0>
-constexpr bool fused_ok() { return rows_t_ok<N, R0>() && N / 16 <= 128 && 2 * (2 * N + N / 16) * 8 <= 70 * 1024; }
+constexpr bool fused_ok() { return rows_seg<N, R0>() == 16 && N / 16 <= 128 && 2 * (2 * N + N / 16) * 8 <= 70 * 1024; }
 template <int N, int R0, int R1, int R2>
 static void launch_front_rows_if(const uint8_t* rgb, const DevParams& P, int nimg, const unsigned char* tabs,
                                  const unsigned char* exc, const float2* twp, Workspace& ws, cudaStream_t st) {

@@ -1051,7 +1051,7 @@ __device__ __forceinline__ void cols_write_power(const DevParams& P, int img, in
 // Columns, specialised.  A CTA walks `gpc` consecutive groups of NB contiguous columns of ONE image: the shared
 // bins are zeroed and flushed once per CTA, and while a group's epilogue runs the bulk-copy engine already
 // fetches the next group's columns (into the buffer the last FFT pass no longer reads) and bin-id slices.
-// Requires Hp == N (H % 4 == 0) so that columns and bin-map slices are 16-byte multiples, and a 3-pass plan.
+// Requires Hp == N (H % 4 == 0), cols_t_ok<N, NB>() (16-byte multiples for the bulk copies) and a 3-pass plan.
 // Two CTAs fit an SM either way.  MINB is only the register-allocation hint of __launch_bounds__ (0 = none): measured,
 // the 1080-point kernel is fastest with 1 (58 registers; 0 -> 48 and 2 -> 60 are 1-2 % slower), the longer ones with 2.
 template <int N, int R0, int R1, int R2, int R3, int NB, int MINB, bool WRITE_POWER>
@@ -1076,7 +1076,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_cols_t(DevParams P, const
     const int g_begin = blockIdx.x * gpc, g_end = min(g_begin + gpc, ngroups);
     auto fetch = [&](int g, int slot) {  // thread 0 only
         const int x0 = g * NB, ncol = min(NB, P.fw - x0);
-        const u32 cbytes = (u32)(ncol * N * sizeof(float2)), mbytes = (u32)(ncol * N * sizeof(u16));
+        const u32 cbytes = (u32)(ncol * N * sizeof(float2)), mbytes = ((u32)(ncol * N * sizeof(u16)) + 15u) & ~15u;
         mbar_expect_tx(&bar, cbytes + mbytes);
         bulk_g2s(bufA, specT + ((size_t)img * P.fw + x0) * N, cbytes, &bar);
         bulk_g2s(smap + slot * NB * N, binmapT + (size_t)x0 * N, mbytes, &bar);
@@ -1586,10 +1586,15 @@ template <int N, int R0, int R1, int R2>
 static void launch_rows_t_if(const uint8_t* rgb, const DevParams& P, int nimg, const float2* tw, float2* specT, cudaStream_t st) {
     if constexpr (rows_t_ok<N, R0>()) launch_rows_t<N, R0, R1, R2, 1, 2>(rgb, P, nimg, tw, specT, st);
 }
+// Lengths the specialised column kernel takes: bulk copies need 16-byte multiples.  A column is N * 8 bytes (always one),
+// a column's bin-id slice N * 2 bytes: whole groups of NB slices are a multiple of 16 when NB * N % 8 == 0, and the one
+// partial group at the end of an image has its slice copy rounded up to 16 bytes (the map has the slack, pipeline.cu).
+template <int N, int NB>
+constexpr bool cols_t_ok() { return N % 4 == 0 && (NB * N) % 8 == 0; }
 template <int N, int R0, int R1, int R2, int NB>
 static void launch_cols_t_if(const DevParams& P, int nimg, const float2* tw, const float2* specT, const u16* binmapT,
                              Workspace& ws, float* power_out, cudaStream_t st) {
-    if constexpr (N % 8 == 0) launch_cols_t<N, R0, R1, R2, 1, NB, (N == 1080 ? kColsMinBlocks1080 : 2)>(P, nimg, tw, specT, binmapT, ws, power_out, st);
+    if constexpr (cols_t_ok<N, NB>()) launch_cols_t<N, R0, R1, R2, 1, NB, (N == 1080 ? kColsMinBlocks1080 : 2)>(P, nimg, tw, specT, binmapT, ws, power_out, st);
 }
 
 static int rows_generic_grid(size_t smem, int ngroups, int nimg) {
@@ -1719,7 +1724,7 @@ int phd_launch_fft_cols_blur(const DevParams& P, int nimg, const FftPlan& col, f
     if (P.Hp == P.H) {
         switch (P.H) {
 #define PHD_X(N, R0, R1, R2, NB) \
-    case N: if (N % 8 == 0) { launch_cols_t_if<N, R0, R1, R2, NB>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0; } break;
+    case N: if (cols_t_ok<N, NB>()) { launch_cols_t_if<N, R0, R1, R2, NB>(P, nimg, col.twp, specT, binmapT, ws, power_out, st); return 0; } break;
             PHD_FFT_PLANS(PHD_X)
 #undef PHD_X
         }

@@ -339,7 +339,7 @@ int get_shape(phd_context* ctx, int W, int H, int nr, int na, ShapePlan** out) {
     // one allocation per direction: n twiddles, the pass tables, and for a Bluestein plan the chirp (n) and its transform (m)
     CUDA_TRY(ctx, cudaMalloc(&s.tw_row, sizeof(float2) * (W + pe_row + (s.row.m > 0 ? W + s.row.m : 0))));
     CUDA_TRY(ctx, cudaMalloc(&s.tw_col, sizeof(float2) * (H + pe_col + (s.col.m > 0 ? H + s.col.m : 0))));
-    CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec));
+    CUDA_TRY(ctx, cudaMalloc(&s.binmap, sizeof(u16) * nspec + 16));  // + 16: the column kernel rounds its last slice copy up
     CUDA_TRY(ctx, cudaMalloc(&s.bincount, sizeof(int) * nr * na));
     if (!s.long_row) {
         phd_fill_twiddles(s.tw_row, W, ctx->stream);

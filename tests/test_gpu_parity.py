@@ -62,6 +62,8 @@ def test_report_matches_reference_golden(ctx, oracle, golden, name):
     (700, 525, 1, dict(h_partitions=9, s_partitions=3, v_partitions=4, coverage_thresh=0.9)),
     (1024, 768, 0, dict(downsample_rate=2, radius_partitions=16, angle_partitions=36)),
     (3840, 2160, 1, {}),   # BASELINE config 2: 4K with four salient boxes
+    (1080, 1920, 0, {}),   # portrait 1080p: the row kernel's 8-pixel staging segments
+    (1600, 900, 1, {}),    # 900-point columns: the specialised column kernel with a rounded-up last bin-id slice
     (752, 502, 1, {}),     # 2^4*47 x 2*251: prime factors served by the O(p^2) butterfly of the generic FFT kernels
     (1008, 572, 0, {}),    # 2^4*3^2*7 x 2^2*11*13: register butterflies for the primes 7, 11 and 13
     (646, 456, 1, {}),     # 2*17*19 x 2^3*3*19

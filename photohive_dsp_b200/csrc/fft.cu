@@ -1448,8 +1448,8 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
 
 }  // namespace
 
-// Compile-time specialised transform lengths: X(N, R0, R1, R2, NB).  (Second block: 8K / 5K heights, QHD+, WSXGA+ and a few
-// more display sizes; 7680 has no three-pass plan with radices <= 25 and stays on the runtime-radix kernels.)  One three-pass radix plan per length serves the
+// Compile-time specialised transform lengths: X(N, R0, R1, R2, NB).  (Second and third block: 8K / 5K heights, QHD+, WSXGA+, DCI 4K, 2.7K
+// action-camera frames, 5 / 6 / 18 MP sensors and a few more display sizes; 7680 has no three-pass plan with radices <= 25 and stays on the runtime-radix kernels.)  One three-pass radix plan per length serves the
 // row kernel (image width N: needs N % 16 == 0 and (N / R0) % 16 == 0) and the column kernel (image height N: needs
 // N % 8 == 0; NB = columns per CTA group).  An odd first radix keeps the stride-R0 stores of the first pass conflict
 // free.  BASELINE shapes first, then the usual video and camera sizes in both orientations (1080p, 4K, 12 / 16 / 20 /
@@ -1462,7 +1462,9 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
     X(1600, 25, 8, 8, 2) X(2448, 17, 9, 16, 2) X(3000, 15, 8, 25, 1) X(3024, 21, 12, 12, 1) X(3264, 17, 12, 16, 1)  \
     X(3456, 18, 12, 16, 1) X(3648, 19, 12, 16, 1) X(4032, 21, 12, 16, 1) X(4608, 18, 16, 16, 1) X(5472, 19, 18, 16, 1)  \
     X(4320, 15, 16, 18, 1) X(2880, 15, 12, 16, 1) X(1800, 15, 10, 12, 2) X(3200, 25, 8, 16, 1) X(900, 9, 10, 10, 4)       \
-    X(1680, 15, 16, 7, 2) X(1050, 15, 10, 7, 4) X(1152, 9, 8, 16, 2) X(2400, 15, 10, 16, 1)
+    X(1680, 15, 16, 7, 2) X(1050, 15, 10, 7, 4) X(1152, 9, 8, 16, 2) X(2400, 15, 10, 16, 1)                               \
+    X(4096, 16, 16, 16, 1) X(5184, 18, 18, 16, 1) X(2000, 25, 5, 16, 2) X(2704, 13, 13, 16, 2) X(1520, 19, 5, 16, 4)     \
+    X(2592, 9, 18, 16, 2) X(1944, 9, 12, 18, 2)
 
 static bool special_radices(int n, int r[4]) {
 #define PHD_X(N, R0, R1, R2, NB) if (n == N) { r[0] = R0; r[1] = R1; r[2] = R2; r[3] = 1; return true; }

@@ -532,6 +532,7 @@ def test_general_double_planes_match_oracle(oracle, W, H, kw, nbox):
                                  (1280, 960), (960, 1280), (2160, 3840), (1080, 1920), (4000, 6000), (480, 600), (600, 480),
                                  (7680, 4320), (4320, 7680), (5120, 2880), (3200, 1800), (1800, 3200), (1600, 900),
                                  (1680, 1050), (1050, 1680), (2048, 1152), (2400, 1600), (2880, 1800),   # second block of plans
+                                 (4096, 2160), (5184, 3456), (3000, 2000), (2704, 1520), (1520, 2704), (2592, 1944), (1944, 2592),
                                  (2011, 1511), (1511, 2011), (4030, 3020), (1031, 523),   # prime sides: Bluestein
                                  # sides beyond the shared-memory kernels: four-step transforms through HBM (13000 =
                                  # 104 x 125), and Bluestein around them for a prime side (13003)

@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(256, 3) k_front_rows(const uint8_t* __restrict
 // granularity of k_rows_t, e.g. 1080-pixel portrait rows): same staging, compile-time passes, THREADS threads.
 // gray32 != nullptr: the input is a plane of floats (general-input route: (gray - 0.5) * 255000 of one image) instead
 // of packed bytes.
-template <int NP, int N = 0, int R0 = 1, int R1 = 1, int R2 = 1, int THREADS = 512>
+template <int NP, int N = 0, int R0 = 1, int R1 = 1, int R2 = 1, int THREADS = 512, int R3 = 1>
 __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restrict__ rgb, DevParams P, FftPlan pl,
                                                               float2* __restrict__ specT,
                                                               const float* __restrict__ gray32 = nullptr) {
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(THREADS) k_rows_generic(const uint8_t* __restr
         const float2* z;
         if constexpr (N > 0) {
             // table twiddles here: the product tree measured slower in this variant (3000-pixel rows 55 -> 84 us per image)
-            z = fft_run_t<N, R0, R1, R2, 1, false, THREADS / NP, false>(bufA, bufB, pl.twp, NP, N, N);
+            z = fft_run_t<N, R0, R1, R2, R3, false, THREADS / NP, false>(bufA, bufB, pl.twp, NP, N, N);
             __syncthreads();
         } else {
             z = pl.m > 0 ? fft_run_blue(pl, bufA, bufB, NP, L) : fft_run_rt(pl, bufA, bufB, NP, W);
@@ -1466,9 +1466,17 @@ void launch_cols_t(const DevParams& P, int nimg, const float2* tw, const float2*
     X(4096, 16, 16, 16, 1) X(5184, 18, 18, 16, 1) X(2000, 25, 5, 16, 2) X(2704, 13, 13, 16, 2) X(1520, 19, 5, 16, 4)     \
     X(2592, 9, 18, 16, 2) X(1944, 9, 12, 18, 2)
 
+// Row widths with a compile-time FOUR-pass plan (no three radices <= 25 multiply to them): 8K and 5K frames.  One row pair
+// per CTA in the staged row kernel (two pairs do not fit shared memory), X(N, R0, R1, R2, R3).  As column lengths they run
+// the runtime-radix kernel with the same factors.
+#define PHD_FFT_PLANS4(X) X(7680, 15, 8, 8, 8) X(5120, 5, 16, 8, 8)
+
 static bool special_radices(int n, int r[4]) {
 #define PHD_X(N, R0, R1, R2, NB) if (n == N) { r[0] = R0; r[1] = R1; r[2] = R2; r[3] = 1; return true; }
     PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
+#define PHD_X(N, R0, R1, R2, R3) if (n == N) { r[0] = R0; r[1] = R1; r[2] = R2; r[3] = R3; return true; }
+    PHD_FFT_PLANS4(PHD_X)
 #undef PHD_X
     return false;
 }
@@ -1645,7 +1653,7 @@ static void launch_front_rows_if(const uint8_t* rgb, const DevParams& P, int nim
 
 static bool rows_fast_ok(const DevParams& P) {
     int r[4];
-    return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && special_radices(P.W, r);
+    return P.H % 4 == 0 && P.Hp == P.H && P.aligned16 && special_radices(P.W, r) && r[3] == 1;
 }
 
 // Front end and row FFT of `nimg` images as one launch (see k_front_rows); returns false when this shape / parameter
@@ -1677,6 +1685,18 @@ int phd_launch_fft_rows(const uint8_t* rgb, const DevParams& P, int nimg, const 
 #define PHD_X(N, R0, R1, R2, NB) \
     case N: if (!rows_t_ok<N, R0>()) { launch_rows_staged_if<N, R0, R1, R2>(rgb, P, nimg, row, specT, st); return 0; } break;
         PHD_FFT_PLANS(PHD_X)
+#undef PHD_X
+    }
+    switch (P.W) {
+#define PHD_X(N, R0, R1, R2, R3)                                                                                        \
+    case N: {                                                                                                           \
+        const size_t sm = (size_t)N * 2 * sizeof(float2);                                                               \
+        PHD_ALLOW_SMEM((k_rows_generic<1, N, R0, R1, R2, 512, R3>), 200 * 1024);                                        \
+        k_rows_generic<1, N, R0, R1, R2, 512, R3><<<dim3(rows_generic_grid(sm, P.Hp / 2, nimg), nimg), 512, sm, st>>>(  \
+            rgb, P, row, specT);                                                                                        \
+        return 0;                                                                                                       \
+    }
+        PHD_FFT_PLANS4(PHD_X)
 #undef PHD_X
     }
     size_t smem = (size_t)(row.m > 0 ? row.m : P.W) * 4 * sizeof(float2);  // two row pairs, two buffers (Bluestein: padded)

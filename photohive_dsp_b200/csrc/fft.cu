@@ -23,8 +23,8 @@
 // The *_t kernels are compile-time specialised (length and radix plan as template arguments: radix-15/16/25...
 // register butterflies with folded constants) for the lengths of PHD_FFT_PLANS (BASELINE.json's shapes, video and
 // camera sizes); every other length runs the *_generic kernels (runtime radix list with register butterflies for
-// 2..13, 15..19, 21, 25 and an O(p^2) pass for any other prime p: slow for large p -- a prime side of 2011 pixels costs
-// about a millisecond per image -- but arbitrary crops are served rather than refused).
+// 2..13, 15..19, 21, 25, an O(p^2) pass for any other prime p up to 40 and Bluestein's chirp-z for lengths with a larger
+// prime factor: arbitrary crops are served rather than refused).
 #include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 #include <math.h>
 #include <stdlib.h>
@@ -804,8 +804,9 @@ __global__ void __launch_bounds__(256, 3) k_front_rows(const uint8_t* __restrict
 // spectrum entry of the group leaves as one 32-byte sector (NP = 2) or half a sector (NP = 1: rows of 6401..12800
 // pixels, whose two pairs no longer fit shared memory).  Rows past the image bottom count as gray 0.5 (a zero sequence
 // after the bias) and land in the Hp padding of the transposed spectrum.
-// N > 0: the width is the compile-time length N with plan R0 R1 R2 (widths that have a plan but not the 16-pixel
-// granularity of k_rows_t, e.g. 1080-pixel portrait rows): same staging, compile-time passes, THREADS threads.
+// N > 0: the width is the compile-time length N with plan R0 R1 R2 [R3] -- planned widths that k_rows_t / k_rows_tma do
+// not take: those that are not a multiple of 8 (900, 1050), and the four-pass widths 7680 / 5120 (PHD_FFT_PLANS4, NP = 1):
+// same staging, compile-time passes, THREADS threads.
 // gray32 != nullptr: the input is a plane of floats (general-input route: (gray - 0.5) * 255000 of one image) instead
 // of packed bytes.
 template <int NP, int N = 0, int R0 = 1, int R1 = 1, int R2 = 1, int THREADS = 512, int R3 = 1>
@@ -1616,7 +1617,7 @@ static int rows_generic_grid(size_t smem, int ngroups, int nimg) {
     if (gx > ngroups) gx = ngroups;
     return gx < 1 ? 1 : gx;
 }
-// Lengths with a plan that k_rows_t cannot take (1080, 3000, 600): staged bytes + compile-time passes.
+// Lengths with a plan that the row kernel cannot take (not a multiple of 8: 900, 1050): staged bytes + compile-time passes.
 template <int N, int R0, int R1, int R2>
 static void launch_rows_staged_if(const uint8_t* rgb, const DevParams& P, int nimg, const FftPlan& row, float2* specT,
                                   cudaStream_t st) {

@@ -54,6 +54,9 @@ constexpr int kColsMinBlocks1080 = 1; // register hint of the 1080-point column 
 #ifndef PHD_ROWS_TMA
 #define PHD_ROWS_TMA 1  // row kernel: the transposed spectrum leaves through a TMA tensor store (see rows_walk)
 #endif
+#ifndef PHD_RT_TWPOW
+#define PHD_RT_TWPOW 0   // runtime-radix passes: twiddles by the product tree (measured faster, not accurate enough in Bluestein)
+#endif
 #ifndef PHD_ROWS_PK
 #define PHD_ROWS_PK 0   // row butterflies on the packed FP32x2 pipe
 #endif
@@ -379,7 +382,10 @@ __device__ __forceinline__ void pass_rt(const float2* __restrict__ in, float2* _
         for (int k = 0; k < R; k++) x[k] = a[b + k * m];
         Radix<R, false>::run(x);
         y[R * pps + q] = x[0];
-        if (PHD_ROWS_TWPOW != 0) {  // twiddles of the butterfly from its first table entry (see pass_t)
+        // Table twiddles here.  The product tree of pass_t was 6..12 % faster on these kernels too, but in the Bluestein
+        // route (two transforms and three chirp products per sequence) its few extra ulps per twiddle pushed one low-valued
+        // blur bin of a 358x600 image to 1.5e-4 relative (tools/soak.py, case 86 of seed 21): accuracy first on this path.
+        if (PHD_RT_TWPOW != 0) {
             float2 w[R];
             w[1] = __ldg(&twp[b]);
 #pragma unroll

@@ -1,6 +1,6 @@
 """Randomised parity soak (GPU): random shapes, palette grids, weights, list sizes, downsampling and boxes, the CUDA path
 through the C ABI against the CPU oracle with the tolerances of tests/parity.py.
-  python tools/soak.py [cases=40] [seed=1]"""
+  python tools/soak.py [cases=40] [seed=1]        (PHD_SOAK_PLANNED=1: sides drawn from the compile-time FFT plans)"""
 import os
 import sys
 import traceback
@@ -31,8 +31,12 @@ ctx = Context(0)
 HP = [4, 5, 6, 8, 9, 10, 12, 15, 18, 20, 24, 30, 36, 40, 45, 60, 72]
 bad = 0
 for case in range(ncases):
-    W = int(rng.integers(350, 1400))
-    H = int(rng.integers(max(350, W // 4), min(1400, W * 4)))
+    if os.environ.get("PHD_SOAK_PLANNED"):  # shapes whose sides have compile-time FFT plans (the specialised kernels)
+        sides = [480, 600, 640, 720, 768, 800, 900, 960, 1024, 1080, 1152, 1200, 1280, 1440, 1520, 1536, 1600]
+        W, H = int(rng.choice(sides)), int(rng.choice(sides))
+    else:
+        W = int(rng.integers(350, 1400))
+        H = int(rng.integers(max(350, W // 4), min(1400, W * 4)))
     kind = int(rng.integers(0, 3))
     kw = dict(h_partitions=int(rng.choice(HP)), s_partitions=int(rng.integers(1, 5)), v_partitions=int(rng.integers(1, 7)),
               black_thresh=float(rng.choice([0.05, 0.1, 0.2, 0.3])), gray_thresh=float(rng.choice([0.05, 0.1, 0.25])),
